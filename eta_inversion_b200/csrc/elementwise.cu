@@ -1,0 +1,397 @@
+// Data-movement, weight-repack and fused scheduler kernels (HBM / latency bound; vectorised, no atomics).
+#include "ops.cuh"
+
+namespace etai {
+
+// ---------------------------------------------------------------------------------------------
+// layout conversion at the ABI boundary (latents are NCHW [B,4,64,64] in the reference)
+// ---------------------------------------------------------------------------------------------
+template <typename TI, typename TO>
+__global__ void nchw_to_nhwc_k(const TI* __restrict__ in, TO* __restrict__ out, int C, long HW, long total) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;  // index into NHWC output
+    if (i >= total) return;
+    int c = (int)(i % C);
+    long p = (i / C) % HW;
+    long b = i / (C * HW);
+    out[i] = from_f<TO>(to_f<TI>(in[(b * C + c) * HW + p]));
+}
+template <typename TI, typename TO>
+__global__ void nhwc_to_nchw_k(const TI* __restrict__ in, TO* __restrict__ out, int C, long HW, long total) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;  // index into NCHW output
+    if (i >= total) return;
+    long p = i % HW;
+    int c = (int)((i / HW) % C);
+    long b = i / (C * HW);
+    out[i] = from_f<TO>(to_f<TI>(in[(b * HW + p) * C + c]));
+}
+template <typename TI, typename TO>
+__global__ void convert_k(const TI* __restrict__ in, TO* __restrict__ out, long n) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = from_f<TO>(to_f<TI>(in[i]));
+}
+
+#define DISPATCH2(dti, dto, TI, TO, ...) \
+    ETAI_DISPATCH_DTYPE(dti, TI, ETAI_DISPATCH_DTYPE(dto, TO, __VA_ARGS__))
+
+void nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int B, int C, long HW, cudaStream_t s) {
+    long total = (long)B * C * HW;
+    DISPATCH2(in_dtype, out_dtype, TI, TO,
+              (nchw_to_nhwc_k<TI, TO><<<cdiv(total, 256), 256, 0, s>>>((const TI*)in, (TO*)out, C, HW, total)));
+    KERNEL_CHECK();
+}
+void nhwc_to_nchw(const void* in, int in_dtype, void* out, int out_dtype, int B, int C, long HW, cudaStream_t s) {
+    long total = (long)B * C * HW;
+    DISPATCH2(in_dtype, out_dtype, TI, TO,
+              (nhwc_to_nchw_k<TI, TO><<<cdiv(total, 256), 256, 0, s>>>((const TI*)in, (TO*)out, C, HW, total)));
+    KERNEL_CHECK();
+}
+void convert(const void* in, int in_dtype, void* out, int out_dtype, long n, cudaStream_t s) {
+    if (n == 0) return;
+    DISPATCH2(in_dtype, out_dtype, TI, TO,
+              (convert_k<TI, TO><<<cdiv(n, 256), 256, 0, s>>>((const TI*)in, (TO*)out, n)));
+    KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------
+// channel concat (skip connections), nearest 2x upsample, im2col for stride-2 convs. 16-byte vectors.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void concat_k(const T* __restrict__ a, int Ca, const T* __restrict__ b, int Cb, T* __restrict__ out,
+                         long rows) {
+    constexpr int V = 16 / sizeof(T);
+    int Cv = (Ca + Cb) / V, Cav = Ca / V;
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= rows * Cv) return;
+    long r = i / Cv;
+    int cv = (int)(i % Cv);
+    const uint4* src = cv < Cav ? reinterpret_cast<const uint4*>(a + r * Ca) + cv
+                                : reinterpret_cast<const uint4*>(b + r * Cb) + (cv - Cav);
+    reinterpret_cast<uint4*>(out + r * (long)(Ca + Cb))[cv] = *src;
+}
+void concat_channels(const void* a, int Ca, const void* b, int Cb, void* out, long rows, int dtype, cudaStream_t s) {
+    ETAI_DISPATCH_DTYPE(dtype, T, {
+        constexpr int V = 16 / sizeof(T);
+        ETAI_CHECK(Ca % V == 0 && Cb % V == 0, ETAI_ERR_ARG, "concat: channels must be multiples of 16 bytes");
+        long n = rows * ((Ca + Cb) / V);
+        concat_k<T><<<cdiv(n, 256), 256, 0, s>>>((const T*)a, Ca, (const T*)b, Cb, (T*)out, rows);
+    });
+    KERNEL_CHECK();
+}
+
+template <typename T>
+__global__ void upsample2x_k(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C, long total) {
+    constexpr int V = 16 / sizeof(T);
+    int Cv = C / V;
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int cv = (int)(i % Cv);
+    long p = i / Cv;
+    int ox = (int)(p % (2 * W));
+    int oy = (int)((p / (2 * W)) % (2 * H));
+    long b = p / (4L * W * H);
+    const uint4* src = reinterpret_cast<const uint4*>(in + ((b * H + oy / 2) * W + ox / 2) * (long)C) + cv;
+    reinterpret_cast<uint4*>(out)[i] = *src;
+}
+void upsample2x(const void* in, void* out, int B, int H, int W, int C, int dtype, cudaStream_t s) {
+    ETAI_DISPATCH_DTYPE(dtype, T, {
+        constexpr int V = 16 / sizeof(T);
+        ETAI_CHECK(C % V == 0, ETAI_ERR_ARG, "upsample: C must be a multiple of 16 bytes");
+        long total = (long)B * 4 * H * W * (C / V);
+        upsample2x_k<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)in, (T*)out, H, W, C, total);
+    });
+    KERNEL_CHECK();
+}
+
+template <typename T>
+__global__ void im2col3x3_k(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C, int stride, int Ho,
+                            int Wo, long total) {
+    constexpr int V = 16 / sizeof(T);
+    int Cv = C / V;
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int cv = (int)(i % Cv);
+    long r = i / Cv;
+    int tap = (int)(r % 9);
+    long m = r / 9;
+    int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho);
+    long b = m / ((long)Wo * Ho);
+    int iy = oy * stride + tap / 3 - 1, ix = ox * stride + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+        v = reinterpret_cast<const uint4*>(in + ((b * H + iy) * W + ix) * (long)C)[cv];
+    reinterpret_cast<uint4*>(out)[i] = v;
+}
+void im2col3x3(const void* in, void* out, int B, int H, int W, int C, int stride, int Ho, int Wo, int dtype,
+               cudaStream_t s) {
+    ETAI_DISPATCH_DTYPE(dtype, T, {
+        constexpr int V = 16 / sizeof(T);
+        ETAI_CHECK(C % V == 0, ETAI_ERR_ARG, "im2col: C must be a multiple of 16 bytes");
+        long total = (long)B * Ho * Wo * 9 * (C / V);
+        im2col3x3_k<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)in, (T*)out, H, W, C, stride, Ho, Wo, total);
+    });
+    KERNEL_CHECK();
+}
+
+// rows [dst_row, dst_row+n_dst) := rows [src_row, src_row+n_src) tiled (PnP feature injection)
+template <typename T>
+__global__ void copy_rows_k(T* base, long row_vecs, int src_row, int n_src, int dst_row, long total) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    long r = i / row_vecs, v = i % row_vecs;
+    uint4* b4 = reinterpret_cast<uint4*>(base);
+    b4[(dst_row + r) * row_vecs + v] = b4[(src_row + r % n_src) * row_vecs + v];
+}
+void copy_rows(void* base, long row_elems, int src_row, int n_src, int dst_row, int n_dst, int dtype, cudaStream_t s) {
+    ETAI_DISPATCH_DTYPE(dtype, T, {
+        constexpr int V = 16 / sizeof(T);
+        ETAI_CHECK(row_elems % V == 0, ETAI_ERR_ARG, "copy_rows: row must be a multiple of 16 bytes");
+        long total = (long)n_dst * (row_elems / V);
+        copy_rows_k<T><<<cdiv(total, 256), 256, 0, s>>>((T*)base, row_elems / V, src_row, n_src, dst_row, total);
+    });
+    KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------
+// time embedding: [cos(t f_i), sin(t f_i)], f_i = exp(-ln(1e4) i / half)  (flip_sin_to_cos=True, shift 0)
+// ---------------------------------------------------------------------------------------------
+__global__ void timestep_sincos_k(float t, float* out, int half) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    float f = expf(-9.210340371976184f * (float)i / (float)half);
+    float a = t * f;
+    out[i] = cosf(a);
+    out[half + i] = sinf(a);
+}
+void timestep_sincos(float t, float* out, int dim, cudaStream_t s) {
+    timestep_sincos_k<<<cdiv(dim / 2, 128), 128, 0, s>>>(t, out, dim / 2);
+    KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------
+// skinny linear: tiny M (time MLP, per-resnet time projections). One warp per output column,
+// weights streamed once with 16-byte loads; bandwidth bound on W.
+// ---------------------------------------------------------------------------------------------
+template <typename TW, int MAXM>
+__global__ void skinny_linear_k(const float* __restrict__ x, const TW* __restrict__ W, const TW* __restrict__ bias,
+                                float* __restrict__ out, int M, int N, int K, int act) {
+    int n = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    int lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float acc[MAXM];
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) acc[m] = 0.f;
+    const TW* w = W + (long)n * K;
+    for (int k = lane * 8; k < K; k += 256) {
+        float wv[8];
+        load8<TW>(w + k, wv);
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) {
+            if (m < M) {
+                float xv[8];
+                load8<float>(x + (long)m * K + k, xv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[m] = fmaf(wv[j], xv[j], acc[m]);
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+        if (m < M) {
+            float v = warp_sum(acc[m]);
+            if (lane == 0) {
+                if (bias) v += to_f<TW>(bias[n]);
+                if (act == 1) v = silu_f(v);
+                out[(long)m * N + n] = v;
+            }
+        }
+    }
+}
+void skinny_linear(const float* x, const void* W, const void* bias, float* out, int M, int N, int K, int act,
+                   int wdtype, cudaStream_t s) {
+    ETAI_CHECK(M <= 8 && K % 8 == 0, ETAI_ERR_ARG, "skinny_linear: M<=8 and K%8==0 required");
+    ETAI_DISPATCH_DTYPE(wdtype, TW, (skinny_linear_k<TW, 8><<<cdiv(N, 8), 256, 0, s>>>(
+                                        x, (const TW*)W, (const TW*)bias, out, M, N, K, act)));
+    KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight repack (runs once at create): OIHW fp32 -> [O][ky][kx][I] T ; GEGLU row interleave
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_conv_k(const float* __restrict__ w, T* __restrict__ out, int O, int I, long total) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;  // index into output [O][9][I]
+    if (i >= total) return;
+    int c = (int)(i % I);
+    int tap = (int)((i / I) % 9);
+    long o = i / (9L * I);
+    out[i] = from_f<T>(w[(o * I + c) * 9 + tap]);
+}
+void pack_conv_weight(const float* oihw, void* out, int O, int I, int dtype, cudaStream_t s) {
+    long total = 9L * O * I;
+    ETAI_DISPATCH_DTYPE(dtype, T, (pack_conv_k<T><<<cdiv(total, 256), 256, 0, s>>>(oihw, (T*)out, O, I, total)));
+    KERNEL_CHECK();
+}
+// ff.net.0.proj: rows [0,N2/2) are the value half, [N2/2,N2) the gate half (chunk(2,-1)). Interleave so that the
+// GEMM epilogue sees (value_j, gate_j) in adjacent columns 2j, 2j+1.
+template <typename T>
+__global__ void pack_geglu_k(const float* __restrict__ w, const float* __restrict__ b, T* __restrict__ wout,
+                             T* __restrict__ bout, int N2, int K, long total) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    int k = (int)(i % K);
+    int r = (int)(i / K);  // output row
+    int src = (r & 1) ? N2 / 2 + r / 2 : r / 2;
+    wout[i] = from_f<T>(w[(long)src * K + k]);
+    if (k == 0) bout[r] = from_f<T>(b[src]);
+}
+void pack_geglu_weight(const float* w, const float* b, void* wout, void* bout, int N2, int K, int dtype,
+                       cudaStream_t s) {
+    long total = (long)N2 * K;
+    ETAI_DISPATCH_DTYPE(dtype, T,
+                        (pack_geglu_k<T><<<cdiv(total, 256), 256, 0, s>>>(w, b, (T*)wout, (T*)bout, N2, K, total)));
+    KERNEL_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused CFG + (eta-)DDIM step (+ noise pick, eta map, source-row pin).  See include/etai.h.
+// Latent-sized (E = 16384 per row): one float4 per thread; the K-way argmin is recomputed per thread from the
+// K losses (K = 10) so no second launch or host sync (reference: argmin().item(), eta_inversion.py:363).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int argmin_first(const float* __restrict__ losses, int K) {
+    // torch.argmin semantics: first minimal index; NaN counts as minimal (eta==0 => 0/0, eta_inversion.py:315)
+    int best = 0;
+    float bv = losses[0];
+    if (bv != bv) return 0;
+    for (int k = 1; k < K; ++k) {
+        float v = losses[k];
+        if (v != v) return k;
+        if (v < bv) { bv = v; best = k; }
+    }
+    return best;
+}
+
+struct StepCoef {
+    float inv_sqrt_a_from, sqrt_1m_a_from, sqrt_a_to, one_m_a_to, sqrt_var;
+};
+
+__global__ void cfg_ddim_step_k(const float4* __restrict__ eps, int n, int has_cfg, float g, const float4* __restrict__ x,
+                                float4* __restrict__ x_out, float4* __restrict__ eps_out, StepCoef c, float eta,
+                                const float4* __restrict__ eta_map, const float4* __restrict__ noise_cand,
+                                const float* __restrict__ losses, int K, const float4* __restrict__ pin_src, long E4) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= (long)n * E4) return;
+    long r = i / E4, e = i % E4;
+    float4 ev;
+    if (has_cfg) {
+        float4 u = eps[i], t = eps[(long)n * E4 + i];
+        ev = make_float4(u.x + g * (t.x - u.x), u.y + g * (t.y - u.y), u.z + g * (t.z - u.z), u.w + g * (t.w - u.w));
+    } else {
+        ev = eps[i];
+    }
+    if (eps_out) eps_out[i] = ev;
+    if (pin_src && r == 0) {  // source row is overwritten by the stored inversion latent
+        x_out[i] = pin_src[e];
+        return;
+    }
+    float4 xv = x[i];
+    float4 em = eta_map ? eta_map[e] : make_float4(1.f, 1.f, 1.f, 1.f);
+    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (noise_cand && eta > 0.f) {
+        int pick = (losses && K > 1) ? argmin_first(losses, K) : 0;
+        z = noise_cand[(long)pick * E4 + e];
+    }
+    auto f = [&](float xx, float ee, float mm, float zz) {
+        float x0 = (xx - c.sqrt_1m_a_from * ee) * c.inv_sqrt_a_from;
+        float sigma = eta * mm * c.sqrt_var;
+        float dir = sqrtf(c.one_m_a_to - sigma * sigma) * ee;
+        return c.sqrt_a_to * x0 + dir + sigma * zz;
+    };
+    x_out[i] = make_float4(f(xv.x, ev.x, em.x, z.x), f(xv.y, ev.y, em.y, z.y), f(xv.z, ev.z, em.z, z.z),
+                           f(xv.w, ev.w, em.w, z.w));
+}
+
+static StepCoef make_coef(float a_from, float a_to, float variance) {
+    StepCoef c;
+    c.inv_sqrt_a_from = (float)(1.0 / sqrt((double)a_from));
+    c.sqrt_1m_a_from = (float)sqrt(1.0 - (double)a_from);
+    c.sqrt_a_to = (float)sqrt((double)a_to);
+    c.one_m_a_to = 1.0f - a_to;
+    c.sqrt_var = (float)sqrt((double)(variance > 0.f ? variance : 0.f));
+    return c;
+}
+
+void cfg_ddim_step(const float* eps, int n, int has_cfg, float guidance, const float* x, float* x_out,
+                   float* eps_cfg_out, float a_from, float a_to, float eta, float variance, const float* eta_map,
+                   const float* noise_cand, const float* losses, int K, const float* pin_src, long E, cudaStream_t s) {
+    ETAI_CHECK(E % 4 == 0, ETAI_ERR_ARG, "scheduler step: row size must be a multiple of 4");
+    long total = (long)n * (E / 4);
+    cfg_ddim_step_k<<<cdiv(total, 256), 256, 0, s>>>(
+        (const float4*)eps, n, has_cfg, guidance, (const float4*)x, (float4*)x_out, (float4*)eps_cfg_out,
+        make_coef(a_from, a_to, variance), eta, (const float4*)eta_map, (const float4*)noise_cand, losses, K,
+        (const float4*)pin_src, E / 4);
+    KERNEL_CHECK();
+}
+
+// losses[k] = mean_e (z_k[e] - z*[e])^2 ; one CTA per candidate, fixed-order tree reduction (deterministic).
+__global__ void __launch_bounds__(512) eta_noise_losses_k(const float* __restrict__ eps, int n, int has_cfg, float g,
+                                                         const float* __restrict__ x,
+                                                         const float* __restrict__ x_prev_inv, StepCoef c, float eta,
+                                                         const float* __restrict__ cand, long E,
+                                                         float* __restrict__ losses) {
+    int k = blockIdx.x;
+    float sigma = eta * c.sqrt_var;
+    float dirc = sqrtf(c.one_m_a_to - sigma * sigma);
+    float acc = 0.f;
+    for (long e = threadIdx.x; e < E; e += blockDim.x) {
+        float ev = has_cfg ? eps[e] + g * (eps[(long)n * E + e] - eps[e]) : eps[e];
+        float x0 = (x[e] - c.sqrt_1m_a_from * ev) * c.inv_sqrt_a_from;
+        float rec = c.sqrt_a_to * x0 + dirc * ev;        // step(eps, eta, z = 0)
+        float zopt = (x_prev_inv[e] - rec) / sigma;      // eta == 0 -> inf/nan exactly like the reference
+        float d = cand[(long)k * E + e] - zopt;
+        acc = fmaf(d, d, acc);
+    }
+    __shared__ float red[16];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) losses[k] = v / (float)E;
+    }
+}
+__global__ void argmin_k(const float* losses, int K, int* best) { *best = argmin_first(losses, K); }
+
+void eta_noise_losses(const float* eps, int n, int has_cfg, float guidance, const float* x, const float* x_prev_inv,
+                      float a_from, float a_to, float eta, float variance, const float* noise_cand, int K, long E,
+                      float* losses, int* best_idx, cudaStream_t s) {
+    eta_noise_losses_k<<<K, 512, 0, s>>>(eps, n, has_cfg, guidance, x, x_prev_inv, make_coef(a_from, a_to, variance),
+                                         eta, noise_cand, E, losses);
+    KERNEL_CHECK();
+    if (best_idx) {
+        argmin_k<<<1, 1, 0, s>>>(losses, K, best_idx);
+        KERNEL_CHECK();
+    }
+}
+
+}  // namespace etai
+
+namespace etai {
+// y += x (used only where an epilogue fusion is impossible, e.g. PnP feature injection between conv2 and the skip add)
+template <typename T>
+__global__ void add_inplace_k(T* __restrict__ y, const T* __restrict__ x, long nvec) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    float a[8], b[8];
+    load8<T>(y + i * 8, a);
+    load8<T>(x + i * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    store8<T>(y + i * 8, a);
+}
+void add_inplace(void* y, const void* x, long n, int dtype, cudaStream_t s) {
+    ETAI_CHECK(n % 8 == 0, ETAI_ERR_ARG, "add_inplace: n%8");
+    ETAI_DISPATCH_DTYPE(dtype, T, (add_inplace_k<T><<<cdiv(n / 8, 256), 256, 0, s>>>((T*)y, (const T*)x, n / 8)));
+    KERNEL_CHECK();
+}
+}  // namespace etai

@@ -1,0 +1,320 @@
+// tcgen05 / TMEM / TMA GEMM and implicit-GEMM conv3x3 for sm_100a (f16 / bf16 in, fp32 accumulate in TMEM).
+//
+//   C[M,N] = A[M,K] * W[N,K]^T  + bias[N] + bias2[N](fp32) + residual[M,N]      (or GEGLU epilogue)
+//
+// A is either a dense K-major matrix (2-D tensor map) or, for the 3x3 / pad 1 / stride 1 convolution, the NHWC image
+// itself read through a 4-D tensor map {C, W, H, B}: for every filter tap the producer shifts the box origin by
+// (kx-1, ky-1) and TMA zero-fills the halo, so im2col is never materialised.  One 128-row M tile is a box of
+// bw x bh x bb = 128 output pixels (64x2, 32x4, 16x8 or 8x8x2 images), which lands in shared memory in exactly the
+// K-major / 128B-swizzled layout the UMMA descriptor expects.
+//
+// CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global).  smem ring of STAGES x (A 128x64 + B BNx64).
+// UMMA shape 128 x BN x 16 (cta_group::1), BN in {128, 160}.  Roofline: tensor pipe.
+#include <mutex>
+#include <cstring>
+#include "ops.cuh"
+#include "tc_common.cuh"
+
+namespace etai {
+
+namespace tc {
+
+EncodeTiledFn get_encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+        if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    if (!fn) throw Error(ETAI_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    return fn;
+}
+
+CUtensorMap make_tmap_16bit(const void* base, int dtype, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                            const uint32_t* box) {
+    CUtensorMap m;
+    cuuint64_t gdim[5], gstr[5];
+    cuuint32_t b[5], estr[5];
+    for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; b[i] = box[i]; estr[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUresult r = get_encode_tiled()(&m, dtype == ETAI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                                    (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, b, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error(ETAI_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+    return m;
+}
+
+}  // namespace tc
+
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16, GT_THREADS = 192;
+
+struct TcParams {
+    void* C;
+    const void* bias;      // [N] storage dtype or null
+    const float* bias2;    // [N] fp32 or null (time-embedding projection)
+    const void* residual;  // [M,ldr] or null
+    long M;
+    int N;
+    long ldc, ldr;
+    int geglu;
+    int num_kb;            // K blocks of 64
+    // conv geometry
+    int cin_blocks;        // Cin / 64
+    int Himg, Wimg;        // output == input spatial size (stride 1)
+    int bw, bh, bb;        // box in pixels
+    int fmt;               // 0 f16, 1 bf16
+};
+
+template <int BN>
+struct Smem {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + slack for manual 1024-B alignment
+    static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+};
+
+template <typename T, int BN, bool CONV>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+    using S = Smem<BN>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* empty = full + S::STAGES;
+    uint64_t* accum_full = empty + S::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const long m0 = (long)blockIdx.y * BM;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(accum_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            int b0 = 0, oy0 = 0;
+            if (CONV) {
+                long hw = (long)p.Himg * p.Wimg;
+                b0 = (int)(m0 / hw);
+                oy0 = (int)((m0 % hw) / p.Wimg);
+            }
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                int s = kb % S::STAGES;
+                uint32_t ph = (kb / S::STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], S::STAGE_BYTES);
+                unsigned char* sa = smem + s * S::STAGE_BYTES;
+                unsigned char* sb = sa + S::A_BYTES;
+                if (CONV) {
+                    int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
+                    tma_load_4d(sa, &tmA, &full[s], cb * BK, tap % 3 - 1, oy0 + tap / 3 - 1, b0);
+                } else {
+                    tma_load_2d(sa, &tmA, &full[s], kb * BK, (int)m0);
+                }
+                tma_load_2d(sb, &tmB, &full[s], kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc = make_idesc_f16(p.fmt, BM, BN);
+            for (int kb = 0; kb < p.num_kb; ++kb) {
+                int s = kb % S::STAGES;
+                uint32_t ph = (kb / S::STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES);
+                uint64_t da = make_smem_desc_sw128(sa);
+                uint64_t db = make_smem_desc_sw128(sa + S::A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    // advance 16 elements (32 B) along K inside the 128-B swizzle atom: +2 in the (addr>>4) field
+                    umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty[s]);  // frees the smem stage once these MMAs retire
+            }
+            umma_commit(accum_full);
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        mbar_wait(accum_full, 0);
+        tc_fence_after();
+        const int quarter = warp & 3;
+        const long m = m0 + quarter * 32 + lane;
+        const bool row_ok = m < p.M;
+        T* C = reinterpret_cast<T*>(p.C);
+        const T* bias = reinterpret_cast<const T*>(p.bias);
+        const T* res = reinterpret_cast<const T*>(p.residual);
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);  // warp-collective
+            const int n = n0 + c0;
+            if (!row_ok || n >= p.N) continue;
+            if (bias) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float b8[8];
+                    load8<T>(bias + n + j, b8);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[j + i] += b8[i];
+                }
+            }
+            if (p.bias2) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 b4 = *reinterpret_cast<const float4*>(p.bias2 + n + j);
+                    v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                }
+            }
+            if (p.geglu) {
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_f(v[2 * j + 1]);
+                T* dst = C + m * p.ldc + n / 2;
+#pragma unroll
+                for (int j = 0; j < 16; j += 8) {
+                    float o8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o8[i] = o[j + i];
+                    store8<T>(dst + j, o8);
+                }
+            } else {
+                if (res) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float r8[8];
+                        load8<T>(res + m * p.ldr + n + j, r8);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[j + i] += r8[i];
+                    }
+                }
+                T* dst = C + m * p.ldc + n;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float o8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) o8[i] = v[j + i];
+                    store8<T>(dst + j, o8);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+template <typename T, int BN, bool CONV>
+void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
+    using S = Smem<BN>;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_k<T, BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        configured = true;
+    }
+    dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM));
+    gemm_tc_k<T, BN, CONV><<<grid, GT_THREADS, S::TOTAL, s>>>(tmA, tmB, p);
+    KERNEL_CHECK();
+}
+
+}  // namespace
+
+bool gemm_tc_supported(const GemmArgs& a) {
+    if (a.dtype != ETAI_F16 && a.dtype != ETAI_BF16) return false;
+    if (a.N % 32 != 0 || a.M < 1) return false;
+    if (a.rowbias && a.rows_per_group < a.M) return false;  // only a single shared fp32 bias vector is fused
+    if (a.geglu && a.N % 64 != 0) return false;
+    if (a.conv) {
+        if (a.Cin % 64 != 0) return false;
+        if (a.stride == 1) {
+            int W = a.Wd, H = a.H;
+            if (W > 128 || 128 % W != 0) return false;
+            int bh = 128 / W < H ? 128 / W : H;
+            if (H % bh != 0) return false;
+            return true;
+        }
+        return a.stride == 2;  // im2col + dense
+    }
+    return a.K % 64 == 0 && a.lda % 8 == 0 && a.lda >= a.K;
+}
+
+void gemm_tc(const GemmArgs& a0, void* ws, size_t ws_bytes, cudaStream_t s) {
+    ETAI_CHECK(gemm_tc_supported(a0), ETAI_ERR_UNSUPPORTED, "gemm_tc: unsupported problem");
+    GemmArgs a = a0;
+    if (a.conv && a.stride == 2) {
+        // the three downsample convs (0.7% of UNet FLOPs): gather to [M, 9*Cin] once, then a dense GEMM
+        size_t need = (size_t)a.M * 9 * a.Cin * 2;
+        ETAI_CHECK(ws && ws_bytes >= need, ETAI_ERR_ARG, "gemm_tc: stride-2 conv needs an im2col workspace");
+        im2col3x3(a.A, ws, a.B, a.H, a.Wd, a.Cin, 2, a.Ho, a.Wo, a.dtype, s);
+        a.A = ws; a.conv = 0; a.lda = 9L * a.Cin; a.K = 9 * a.Cin;
+    }
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.C = a.C; p.bias = a.bias; p.bias2 = (const float*)a.rowbias; p.residual = a.residual;
+    p.M = a.M; p.N = a.N; p.ldc = a.ldc; p.ldr = a.ldr; p.geglu = a.geglu;
+    p.fmt = a.dtype == ETAI_BF16 ? 1 : 0;
+    const int BN = (a.N % 160 == 0) ? 160 : 128;
+
+    CUtensorMap tmA, tmB;
+    {
+        uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
+        uint64_t str[1] = {(uint64_t)a.K * 2};
+        uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+        tmB = make_tmap_16bit(a.W, a.dtype, 2, dims, str, box);
+    }
+    if (a.conv) {
+        int W = a.Wd, H = a.H;
+        int bw = W, bh = 128 / W < H ? 128 / W : H, bb = 128 / (bw * bh);
+        uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)W, (uint64_t)H, (uint64_t)a.B};
+        uint64_t str[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.Cin * 2 * W, (uint64_t)a.Cin * 2 * W * H};
+        uint32_t box[4] = {(uint32_t)BK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
+        tmA = make_tmap_16bit(a.A, a.dtype, 4, dims, str, box);
+        p.cin_blocks = a.Cin / BK; p.num_kb = 9 * p.cin_blocks;
+        p.Himg = H; p.Wimg = W; p.bw = bw; p.bh = bh; p.bb = bb;
+    } else {
+        uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
+        uint64_t str[1] = {(uint64_t)a.lda * 2};
+        uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
+        tmA = make_tmap_16bit(a.A, a.dtype, 2, dims, str, box);
+        p.num_kb = a.K / BK;
+    }
+#define LAUNCH(T)                                                            \
+    do {                                                                     \
+        if (BN == 160) {                                                     \
+            if (a.conv) launch<T, 160, true>(tmA, tmB, p, s);                \
+            else launch<T, 160, false>(tmA, tmB, p, s);                      \
+        } else {                                                             \
+            if (a.conv) launch<T, 128, true>(tmA, tmB, p, s);                \
+            else launch<T, 128, false>(tmA, tmB, p, s);                      \
+        }                                                                    \
+    } while (0)
+    if (a.dtype == ETAI_F16) LAUNCH(__half);
+    else LAUNCH(__nv_bfloat16);
+#undef LAUNCH
+}
+
+}  // namespace etai

@@ -1,0 +1,104 @@
+// Internal op launchers (host side). All tensors are device pointers; NHWC / row-major.
+#pragma once
+#include "common.cuh"
+
+namespace etai {
+
+// ---------------- GEMM-shaped ops -------------------------------------------------------------
+// C[M,N] = A * W^T (+ epilogue).  A is either a dense [M,K] matrix (lda) or the implicit im2col view of an
+// NHWC image for a 3x3/pad-1 convolution (K = 9*Cin, k = (ky*3+kx)*Cin + c).
+struct GemmArgs {
+    const void* A = nullptr;   // dense: [M,lda]; conv: NHWC image [B,H,W,Cin]
+    const void* W = nullptr;   // [N,K] row-major (K contiguous)
+    void* C = nullptr;         // [M,ldc]  (geglu: [M, N/2] with ldc)
+    const void* bias = nullptr;      // [N] or null
+    const void* rowbias = nullptr;   // [M/rows_per_group, ldrb] fp32, added per (group,n); null = none
+    const void* residual = nullptr;  // [M,ldr] or null
+    long M = 0;
+    int N = 0, K = 0;
+    long lda = 0, ldc = 0, ldr = 0, ldrb = 0;
+    long rows_per_group = 1;
+    int geglu = 0;
+    // conv geometry (conv != 0)
+    int conv = 0, B = 0, H = 0, Wd = 0, Cin = 0, stride = 1, Ho = 0, Wo = 0;
+    int dtype = ETAI_F32;
+};
+
+void gemm_simt(const GemmArgs& a, cudaStream_t s);
+// tcgen05/TMA path (f16/bf16 only).  `ws` is scratch for stride-2 im2col (may be null when not needed).
+void gemm_tc(const GemmArgs& a, void* ws, size_t ws_bytes, cudaStream_t s);
+bool gemm_tc_supported(const GemmArgs& a);
+
+// out[M,N] = act(x[M,K] (fp32) * W[N,K]^T (T) + bias) for tiny M (<=8); fp32 output. act: 0 none, 1 SiLU
+void skinny_linear(const float* x, const void* W, const void* bias, float* out, int M, int N, int K, int act,
+                   int wdtype, cudaStream_t s);
+
+// ---------------- normalisation ---------------------------------------------------------------
+size_t groupnorm_workspace_bytes(int B, long HW, int C, int groups);
+void groupnorm(const void* x, void* y, const void* gamma, const void* beta, int B, long HW, int C, int groups,
+               float eps, bool silu, int dtype, void* ws, cudaStream_t s);
+void layernorm(const void* x, void* y, const void* gamma, const void* beta, long M, int C, float eps, int dtype,
+               cudaStream_t s);
+
+// ---------------- attention -------------------------------------------------------------------
+struct RowMap {  // passed by value to kernels
+    int q[ETAI_MAX_ROWS], k[ETAI_MAX_ROWS], v[ETAI_MAX_ROWS];
+};
+struct SelfAttnArgs {
+    const void *q, *k, *v;  // [B,N,ld*]; head h at column h*d
+    void* out;              // [B,Nq,ldo]
+    int B, Nq, Nk, heads, d;
+    long ldq, ldk, ldv, ldo;
+    float scale;
+    RowMap map;
+    int dtype;
+};
+void attention_simt(const SelfAttnArgs& a, cudaStream_t s);
+void attention_tc(const SelfAttnArgs& a, cudaStream_t s);
+bool attention_tc_supported(const SelfAttnArgs& a);
+
+// cross attention over the 77-token text context with the prompt-to-prompt edit + store fused in
+struct CrossGroup {  // one CTA-column of work: a plain row (tgt<0) or a (base,tgt) pair
+    int base, tgt, pair;      // UNet batch rows; pair = index into the edit tables
+    int store_base, store_tgt;  // slot in the store accumulators or -1
+};
+struct CrossAttnArgs {
+    const void* q;   // [B,N,ldq]
+    const void* kv;  // [B,L,ldkv]: K at column koff + h*d, V at column voff + h*d
+    void* out;       // [B,N,ldo]
+    int B, N, L, heads, d;
+    long ldq, ldkv, ldo;
+    int koff, voff;
+    float scale;
+    int n_groups;
+    CrossGroup groups[ETAI_MAX_ROWS];
+    const float *mapper, *blend_a, *equalizer, *alpha_step;  // per pair tables or null (no edit)
+    float* store;  // [slots][N][L] fp32 accumulators or null
+    int dtype;
+};
+void cross_attention(const CrossAttnArgs& a, cudaStream_t s);
+
+// ---------------- data movement / elementwise -------------------------------------------------
+void nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int B, int C, long HW, cudaStream_t s);
+void nhwc_to_nchw(const void* in, int in_dtype, void* out, int out_dtype, int B, int C, long HW, cudaStream_t s);
+void convert(const void* in, int in_dtype, void* out, int out_dtype, long n, cudaStream_t s);
+void concat_channels(const void* a, int Ca, const void* b, int Cb, void* out, long rows, int dtype, cudaStream_t s);
+void upsample2x(const void* in, void* out, int B, int H, int W, int C, int dtype, cudaStream_t s);
+void im2col3x3(const void* in, void* out, int B, int H, int W, int C, int stride, int Ho, int Wo, int dtype,
+               cudaStream_t s);
+void copy_rows(void* base, long row_elems, int src_row, int n_src, int dst_row, int n_dst, int dtype, cudaStream_t s);
+void timestep_sincos(float t, float* out, int dim, cudaStream_t s);
+void add_inplace(void* y, const void* x, long n, int dtype, cudaStream_t s);
+// weight repack: OIHW -> O,(ky,kx),I ; optional GEGLU row interleave
+void pack_conv_weight(const float* oihw, void* out, int O, int I, int dtype, cudaStream_t s);
+void pack_geglu_weight(const float* w, const float* b, void* wout, void* bout, int N2, int K, int dtype, cudaStream_t s);
+
+// ---------------- scheduler -------------------------------------------------------------------
+void cfg_ddim_step(const float* eps, int n, int has_cfg, float guidance, const float* x, float* x_out,
+                   float* eps_cfg_out, float a_from, float a_to, float eta, float variance, const float* eta_map,
+                   const float* noise_cand, const float* losses, int K, const float* pin_src, long E, cudaStream_t s);
+void eta_noise_losses(const float* eps, int n, int has_cfg, float guidance, const float* x, const float* x_prev_inv,
+                      float a_from, float a_to, float eta, float variance, const float* noise_cand, int K, long E,
+                      float* losses, int* best_idx, cudaStream_t s);
+
+}  // namespace etai

@@ -1,0 +1,653 @@
+// SD-1.x UNet2DConditionModel as an explicit kernel schedule (NHWC inside, one stream, no host sync).
+//
+// Replaces `model.unet(sample, t, encoder_hidden_states=ctx)["sample"]` of the reference
+// (modules/inversion/diffusion_inversion.py:264-280, eta_inversion.py:321); architecture per SURVEY.md Appendix A
+// (diffusers 0.21.1).  Weight names/layouts are the diffusers state_dict; they are repacked once at create():
+//   conv OIHW -> [O][ky][kx][I] (implicit-GEMM K order), to_q/to_k/to_v of attn1 stacked to one [3C,C] GEMM,
+//   all 16 cross-attention to_k/to_v stacked to one [sum 2C, 768] GEMM that runs once per context,
+//   all 22 time_emb_proj stacked to one skinny GEMM, GEGLU rows interleaved (value,gate) for the fused epilogue.
+#include <unordered_map>
+#include <vector>
+#include <string>
+#include <cstring>
+#include <cmath>
+
+#include "ops.cuh"
+
+namespace etai {
+
+namespace {
+
+struct Conv { void* w = nullptr; void* b = nullptr; int cin = 0, cout = 0; };
+struct Lin { void* w = nullptr; void* b = nullptr; int n = 0, k = 0; };
+struct Norm { void* g = nullptr; void* b = nullptr; int c = 0; };
+struct Res { Norm n1, n2; Conv c1, c2; Lin sc; bool has_sc = false; int cin = 0, cout = 0, temb_off = 0; };
+struct Tfm {
+    Norm gn, ln1, ln2, ln3;
+    Lin pin, qkv, o1, q2, o2, ff1, ff2, pout;
+    int C = 0, index = 0, place = 0, kv_off = 0;  // place: 0 down, 1 mid, 2 up
+};
+
+// fp32 scratch layout of the time-embedding path
+constexpr int TB_SIN = 0, TB_H1 = 4096, TB_ST = 8192, TB_PROJ = 16384;
+
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, off = 0, peak = 0;
+    void* alloc(size_t bytes) {
+        size_t a = (off + 255) & ~size_t(255);
+        off = a + bytes;
+        if (off > peak) peak = off;
+        if (base == nullptr) return reinterpret_cast<void*>(size_t(256));  // planning pass: never dereferenced
+        ETAI_CHECK(off <= cap, ETAI_ERR_NOMEM, "activation arena exhausted");
+        return base + a;
+    }
+    void reset() { off = 0; }
+};
+
+}  // namespace
+
+}  // namespace etai
+
+using namespace etai;
+
+struct etai_unet {
+    etai_unet_cfg cfg;
+    int device = 0;
+    int dt = ETAI_F32;   // storage dtype
+    bool tc = false;     // tcgen05 path enabled
+    size_t esz = 4;
+    std::vector<void*> owned;  // device allocations (weights)
+    size_t weight_bytes = 0;
+
+    Conv conv_in, conv_out;
+    Norm norm_out;
+    Lin time1, time2, temb_all;   // temb_all: stacked time_emb_proj of every resnet
+    Lin kv_all;                   // stacked cross-attention to_k/to_v of every transformer
+    std::vector<Res> down_res[4], up_res[4];
+    std::vector<Tfm> down_tf[4], up_tf[4];
+    Conv down_samp[3], up_samp[3];
+    Res mid_res[2];
+    Tfm mid_tf;
+    int n_tf = 0, temb_total = 0, kv_total = 0;
+
+    // per-forward workspace
+    Arena arena;
+    void* kv_cache = nullptr;  // [max_batch*ctx_len, kv_total]
+    void* ctx_buf = nullptr;   // [max_batch*ctx_len, cross_dim] in storage dtype
+    int ctx_rows = 0;          // batch rows of the cached context (0 = none)
+    float* tbuf = nullptr;     // time embedding scratch (fp32)
+    void* gn_ws = nullptr;
+    void* tc_ws = nullptr;
+    size_t tc_ws_bytes = 0;
+    size_t workspace_bytes = 0;
+
+    // ---- weight loading helpers -------------------------------------------------------------
+    std::unordered_map<std::string, const etai_tensor*> table;
+    float* stage = nullptr;
+    size_t stage_elems = 0;
+
+    void* dmalloc(size_t bytes) {
+        void* p = nullptr;
+        CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 256));
+        owned.push_back(p);
+        weight_bytes += bytes;
+        return p;
+    }
+    const etai_tensor& find(const std::string& name) {
+        auto it = table.find(name);
+        ETAI_CHECK(it != table.end(), ETAI_ERR_ARG, ("missing weight: " + name).c_str());
+        return *it->second;
+    }
+    static size_t numel(const etai_tensor& t) {
+        size_t n = 1;
+        for (int i = 0; i < t.ndim; ++i) n *= (size_t)t.shape[i];
+        return n;
+    }
+    // fp32 copy of a named tensor in the staging buffer (device); valid until the next call
+    const float* staged(const std::string& name, std::initializer_list<int64_t> shape) {
+        const etai_tensor& t = find(name);
+        ETAI_CHECK(t.ndim == (int)shape.size(), ETAI_ERR_ARG, ("bad rank for " + name).c_str());
+        int i = 0;
+        for (int64_t s : shape) {
+            ETAI_CHECK(t.shape[i] == s, ETAI_ERR_ARG, ("bad shape for " + name).c_str());
+            ++i;
+        }
+        size_t n = numel(t);
+        ETAI_CHECK(n <= stage_elems, ETAI_ERR_ARG, "staging buffer too small");
+        if (t.dtype == ETAI_F32) {
+            CUDA_CHECK(cudaMemcpy(stage, t.data, n * 4, t.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+        } else {
+            void* tmp = reinterpret_cast<char*>(stage) + stage_elems * 4;  // second half of the staging area
+            CUDA_CHECK(cudaMemcpy(tmp, t.data, n * 2, t.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+            convert(tmp, t.dtype, stage, ETAI_F32, (long)n, 0);
+            CUDA_CHECK(cudaStreamSynchronize(0));
+        }
+        return stage;
+    }
+    // plain tensor converted to storage dtype at dst (device)
+    void put(const std::string& name, std::initializer_list<int64_t> shape, void* dst) {
+        const float* s = staged(name, shape);
+        size_t n = numel(find(name));
+        convert(s, ETAI_F32, dst, dt, (long)n, 0);
+        CUDA_CHECK(cudaStreamSynchronize(0));
+    }
+    Norm load_norm(const std::string& p, int c) {
+        Norm n;
+        n.c = c;
+        n.g = dmalloc(c * esz);
+        n.b = dmalloc(c * esz);
+        put(p + ".weight", {c}, n.g);
+        put(p + ".bias", {c}, n.b);
+        return n;
+    }
+    Lin load_lin(const std::string& p, int n, int k, bool bias, bool conv1x1 = false) {
+        Lin l;
+        l.n = n; l.k = k;
+        l.w = dmalloc((size_t)n * k * esz);
+        if (conv1x1) put(p + ".weight", {n, k, 1, 1}, l.w);
+        else put(p + ".weight", {n, k}, l.w);
+        if (bias) {
+            l.b = dmalloc(n * esz);
+            put(p + ".bias", {n}, l.b);
+        }
+        return l;
+    }
+    Conv load_conv(const std::string& p, int cin, int cout) {
+        Conv c;
+        c.cin = cin; c.cout = cout;
+        c.w = dmalloc((size_t)cout * 9 * cin * esz);
+        c.b = dmalloc(cout * esz);
+        const float* s = staged(p + ".weight", {cout, cin, 3, 3});
+        pack_conv_weight(s, c.w, cout, cin, dt, 0);
+        CUDA_CHECK(cudaStreamSynchronize(0));
+        put(p + ".bias", {cout}, c.b);
+        return c;
+    }
+    Res load_res(const std::string& p, int cin, int cout, int temb) {
+        Res r;
+        r.cin = cin; r.cout = cout;
+        r.n1 = load_norm(p + ".norm1", cin);
+        r.c1 = load_conv(p + ".conv1", cin, cout);
+        r.n2 = load_norm(p + ".norm2", cout);
+        r.c2 = load_conv(p + ".conv2", cout, cout);
+        r.has_sc = cin != cout;
+        if (r.has_sc) r.sc = load_lin(p + ".conv_shortcut", cout, cin, true, true);
+        // time_emb_proj goes into the stacked matrix
+        r.temb_off = temb_total;
+        put(p + ".time_emb_proj.weight", {cout, temb}, (char*)temb_all.w + (size_t)temb_total * temb * esz);
+        put(p + ".time_emb_proj.bias", {cout}, (char*)temb_all.b + (size_t)temb_total * esz);
+        temb_total += cout;
+        return r;
+    }
+    Tfm load_tfm(const std::string& p, int C, int place) {
+        Tfm t;
+        t.C = C; t.place = place; t.index = n_tf++;
+        const std::string b = p + ".transformer_blocks.0";
+        int X = cfg.cross_dim;
+        t.gn = load_norm(p + ".norm", C);
+        t.pin = load_lin(p + ".proj_in", C, C, true, true);
+        t.ln1 = load_norm(b + ".norm1", C);
+        t.ln2 = load_norm(b + ".norm2", C);
+        t.ln3 = load_norm(b + ".norm3", C);
+        t.qkv.n = 3 * C; t.qkv.k = C;
+        t.qkv.w = dmalloc((size_t)3 * C * C * esz);
+        put(b + ".attn1.to_q.weight", {C, C}, t.qkv.w);
+        put(b + ".attn1.to_k.weight", {C, C}, (char*)t.qkv.w + (size_t)C * C * esz);
+        put(b + ".attn1.to_v.weight", {C, C}, (char*)t.qkv.w + (size_t)2 * C * C * esz);
+        t.o1 = load_lin(b + ".attn1.to_out.0", C, C, true);
+        t.q2 = load_lin(b + ".attn2.to_q", C, C, false);
+        t.kv_off = kv_total;
+        put(b + ".attn2.to_k.weight", {C, X}, (char*)kv_all.w + (size_t)kv_total * X * esz);
+        put(b + ".attn2.to_v.weight", {C, X}, (char*)kv_all.w + (size_t)(kv_total + C) * X * esz);
+        kv_total += 2 * C;
+        t.o2 = load_lin(b + ".attn2.to_out.0", C, C, true);
+        // GEGLU projection with (value,gate) row interleave
+        t.ff1.n = 8 * C; t.ff1.k = C;
+        t.ff1.w = dmalloc((size_t)8 * C * C * esz);
+        t.ff1.b = dmalloc((size_t)8 * C * esz);
+        {
+            const float* w = staged(b + ".ff.net.0.proj.weight", {8 * C, C});
+            // bias staged right behind the weight in the staging buffer
+            const etai_tensor& bt = find(b + ".ff.net.0.proj.bias");
+            ETAI_CHECK(bt.ndim == 1 && bt.shape[0] == 8 * C && bt.dtype == ETAI_F32, ETAI_ERR_ARG, "geglu bias must be fp32 [8C]");
+            float* bs = stage + (size_t)8 * C * C;
+            CUDA_CHECK(cudaMemcpy(bs, bt.data, (size_t)8 * C * 4, bt.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+            pack_geglu_weight(w, bs, t.ff1.w, t.ff1.b, 8 * C, C, dt, 0);
+            CUDA_CHECK(cudaStreamSynchronize(0));
+        }
+        t.ff2 = load_lin(b + ".ff.net.2", C, 4 * C, true);
+        t.pout = load_lin(p + ".proj_out", C, C, true, true);
+        return t;
+    }
+
+    void build(const etai_tensor* weights, int n_weights);
+    void plan_workspace();
+    void set_context(const void* ctx, int io_dtype, int B, cudaStream_t s);
+    void forward(const void* latent, float t, int io_dtype, int B, const etai_attn_ctrl* ctrl, void* eps_out,
+                 cudaStream_t s);
+
+    // ---- op wrappers --------------------------------------------------------------------------
+    void gemm(GemmArgs& a, cudaStream_t s) {
+        a.dtype = dt;
+        if (tc && gemm_tc_supported(a)) gemm_tc(a, tc_ws, tc_ws_bytes, s);
+        else gemm_simt(a, s);
+    }
+    void* linear(const void* x, long M, const Lin& l, const void* residual, cudaStream_t s, int geglu = 0) {
+        int nout = geglu ? l.n / 2 : l.n;
+        void* y = arena.alloc((size_t)M * nout * esz);
+        GemmArgs a;
+        a.A = x; a.W = l.w; a.C = y; a.bias = l.b; a.residual = residual;
+        a.M = M; a.N = l.n; a.K = l.k; a.lda = l.k; a.ldc = nout; a.ldr = nout; a.geglu = geglu;
+        if (arena.base) gemm(a, s);
+        return y;
+    }
+    void* conv3x3(const void* x, int B, int H, int W, const Conv& c, int stride, const float* rowbias,
+                  const void* residual, cudaStream_t s) {
+        int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+        long M = (long)B * Ho * Wo;
+        void* y = arena.alloc((size_t)M * c.cout * esz);
+        GemmArgs a;
+        a.A = x; a.W = c.w; a.C = y; a.bias = c.b; a.residual = residual; a.rowbias = rowbias;
+        a.rows_per_group = M; a.ldrb = 0;
+        a.M = M; a.N = c.cout; a.K = 9 * c.cin; a.ldc = c.cout; a.ldr = c.cout;
+        a.conv = 1; a.B = B; a.H = H; a.Wd = W; a.Cin = c.cin; a.stride = stride; a.Ho = Ho; a.Wo = Wo;
+        if (arena.base) gemm(a, s);
+        return y;
+    }
+    void* gnorm(const void* x, int B, long HW, const Norm& n, float eps, bool silu, cudaStream_t s) {
+        void* y = arena.alloc((size_t)B * HW * n.c * esz);
+        if (arena.base) groupnorm(x, y, n.g, n.b, B, HW, n.c, 32, eps, silu, dt, gn_ws, s);
+        return y;
+    }
+    void* lnorm(const void* x, long M, const Norm& n, cudaStream_t s) {
+        void* y = arena.alloc((size_t)M * n.c * esz);
+        if (arena.base) layernorm(x, y, n.g, n.b, M, n.c, 1e-5f, dt, s);
+        return y;
+    }
+    void* resnet(const void* x, int B, int H, int W, const Res& r, const etai_attn_ctrl* ctrl, bool inject_here,
+                 cudaStream_t s) {
+        long HW = (long)H * W, M = B * HW;
+        void* a1 = gnorm(x, B, HW, r.n1, 1e-5f, true, s);
+        void* h = conv3x3(a1, B, H, W, r.c1, 1, tbuf + TB_PROJ + r.temb_off, nullptr, s);
+        void* a2 = gnorm(h, B, HW, r.n2, 1e-5f, true, s);
+        const void* skip = x;
+        if (r.has_sc) skip = linear(x, M, r.sc, nullptr, s);
+        int inj = (ctrl && inject_here) ? ctrl->conv_inject_rows : 0;
+        if (inj > 0) {
+            // pnp_utils.py:172-177: conv2 output of rows [inj,3inj) := rows [0,inj) BEFORE the skip add
+            ETAI_CHECK(B == 3 * inj, ETAI_ERR_ARG, "pnp injection expects B == 3*inject_rows");
+            void* o = conv3x3(a2, B, H, W, r.c2, 1, nullptr, nullptr, s);
+            if (arena.base) {
+                copy_rows(o, HW * r.cout, 0, inj, inj, 2 * inj, dt, s);
+                add_inplace(o, skip, M * r.cout, dt, s);
+            }
+            return o;
+        }
+        return conv3x3(a2, B, H, W, r.c2, 1, nullptr, skip, s);
+    }
+    void* transformer(const void* x, int B, int H, int W, const Tfm& t, const etai_attn_ctrl* ctrl, cudaStream_t s);
+};
+
+// -------------------------------------------------------------------------------------------------
+void etai_unet::build(const etai_tensor* weights, int n_weights) {
+    for (int i = 0; i < n_weights; ++i) table[weights[i].name] = &weights[i];
+    const int* c = cfg.block_out_channels;
+    const int temb = c[0] * 4, X = cfg.cross_dim;
+    ETAI_CHECK(temb <= 4096, ETAI_ERR_ARG, "time embedding too wide");
+    // staging: largest tensor is 3x3 conv 2*c3 -> c3 (or GEGLU 8C x C) in fp32, plus room for a 16-bit source copy
+    size_t big = (size_t)c[3] * (2 * c[3]) * 9;
+    if ((size_t)8 * c[3] * c[3] + 8 * c[3] > big) big = (size_t)8 * c[3] * c[3] + 8 * c[3];
+    stage_elems = big;
+    CUDA_CHECK(cudaMalloc(&stage, stage_elems * 4 + stage_elems * 2));
+
+    // totals for the stacked matrices
+    int sum_res = 0, sum_c = 0;
+    {
+        int cout = c[0];
+        for (int i = 0; i < 4; ++i) { cout = c[i]; sum_res += 2 * cout; if (i < 3) sum_c += 2 * cout; }
+        sum_res += 2 * c[3]; sum_c += c[3];
+        for (int i = 0; i < 4; ++i) { int co = c[3 - i]; sum_res += 3 * co; if (i > 0) sum_c += 3 * co; }
+    }
+    temb_all.n = sum_res; temb_all.k = temb;
+    temb_all.w = dmalloc((size_t)sum_res * temb * esz);
+    temb_all.b = dmalloc((size_t)sum_res * esz);
+    kv_all.n = 2 * sum_c; kv_all.k = X;
+    kv_all.w = dmalloc((size_t)2 * sum_c * X * esz);
+
+    conv_in = load_conv("conv_in", 4, c[0]);
+    time1 = load_lin("time_embedding.linear_1", temb, c[0], true);
+    time2 = load_lin("time_embedding.linear_2", temb, temb, true);
+    int cout = c[0];
+    for (int i = 0; i < 4; ++i) {
+        int cin = cout;
+        cout = c[i];
+        for (int j = 0; j < 2; ++j) {
+            std::string p = "down_blocks." + std::to_string(i);
+            down_res[i].push_back(load_res(p + ".resnets." + std::to_string(j), j == 0 ? cin : cout, cout, temb));
+            if (i < 3) down_tf[i].push_back(load_tfm(p + ".attentions." + std::to_string(j), cout, 0));
+        }
+        if (i < 3) down_samp[i] = load_conv("down_blocks." + std::to_string(i) + ".downsamplers.0.conv", cout, cout);
+    }
+    mid_res[0] = load_res("mid_block.resnets.0", c[3], c[3], temb);
+    mid_tf = load_tfm("mid_block.attentions.0", c[3], 1);
+    mid_res[1] = load_res("mid_block.resnets.1", c[3], c[3], temb);
+    int rev[4] = {c[3], c[2], c[1], c[0]};
+    cout = rev[0];
+    for (int i = 0; i < 4; ++i) {
+        int prev = cout;
+        cout = rev[i];
+        int cin = rev[i + 1 < 3 ? i + 1 : 3];
+        for (int j = 0; j < 3; ++j) {
+            int skip = j == 2 ? cin : cout, rin = j == 0 ? prev : cout;
+            std::string p = "up_blocks." + std::to_string(i);
+            up_res[i].push_back(load_res(p + ".resnets." + std::to_string(j), rin + skip, cout, temb));
+            if (i > 0) up_tf[i].push_back(load_tfm(p + ".attentions." + std::to_string(j), cout, 2));
+        }
+        if (i < 3) up_samp[i] = load_conv("up_blocks." + std::to_string(i) + ".upsamplers.0.conv", cout, cout);
+    }
+    norm_out = load_norm("conv_norm_out", c[0]);
+    conv_out = load_conv("conv_out", c[0], 4);
+    ETAI_CHECK(temb_total == sum_res && kv_total == 2 * sum_c && n_tf == 16, ETAI_ERR_ARG, "architecture bookkeeping mismatch");
+    CUDA_CHECK(cudaFree(stage));
+    stage = nullptr;
+    table.clear();
+}
+
+void* etai_unet::transformer(const void* x, int B, int H, int W, const Tfm& t, const etai_attn_ctrl* ctrl,
+                             cudaStream_t s) {
+    const int C = t.C, heads = cfg.heads, d = C / heads, L = cfg.ctx_len;
+    const long HW = (long)H * W, M = B * HW;
+    const float scale = 1.0f / sqrtf((float)d);
+    void* g = gnorm(x, B, HW, t.gn, 1e-6f, false, s);
+    void* h = linear(g, M, t.pin, nullptr, s);
+    // ---- self attention ----
+    void* n1 = lnorm(h, M, t.ln1, s);
+    void* qkv = linear(n1, M, t.qkv, nullptr, s);
+    void* ao = arena.alloc((size_t)M * C * esz);
+    if (arena.base) {
+        SelfAttnArgs a;
+        a.q = qkv; a.k = (char*)qkv + (size_t)C * esz; a.v = (char*)qkv + (size_t)2 * C * esz;
+        a.out = ao;
+        a.B = B; a.Nq = (int)HW; a.Nk = (int)HW; a.heads = heads; a.d = d;
+        a.ldq = a.ldk = a.ldv = 3 * C; a.ldo = C; a.scale = scale; a.dtype = dt;
+        bool remap = ctrl && (ctrl->flags & ETAI_CTRL_SELF_REMAP) && ((ctrl->self_layer_mask >> t.index) & 1u) &&
+                     HW <= ctrl->self_max_tokens;
+        for (int r = 0; r < B; ++r) {
+            a.map.q[r] = remap ? ctrl->self_q_row[r] : r;
+            a.map.k[r] = remap ? ctrl->self_k_row[r] : r;
+            a.map.v[r] = remap ? ctrl->self_v_row[r] : r;
+            ETAI_CHECK(a.map.q[r] >= 0 && a.map.q[r] < B && a.map.k[r] >= 0 && a.map.k[r] < B && a.map.v[r] >= 0 &&
+                           a.map.v[r] < B, ETAI_ERR_ARG, "self remap row out of range");
+        }
+        if (tc && attention_tc_supported(a)) attention_tc(a, s);
+        else attention_simt(a, s);
+    }
+    h = linear(ao, M, t.o1, h, s);
+    // ---- cross attention ----
+    void* n2 = lnorm(h, M, t.ln2, s);
+    void* q2 = linear(n2, M, t.q2, nullptr, s);
+    void* co = arena.alloc((size_t)M * C * esz);
+    if (arena.base) {
+        CrossAttnArgs a;
+        memset(&a, 0, sizeof(a));
+        a.q = q2; a.kv = kv_cache; a.out = co;
+        a.B = B; a.N = (int)HW; a.L = L; a.heads = heads; a.d = d;
+        a.ldq = C; a.ldkv = kv_total; a.ldo = C; a.koff = t.kv_off; a.voff = t.kv_off + C; a.scale = scale;
+        a.dtype = dt;
+        int slot_of[ETAI_MAX_ROWS];
+        for (int r = 0; r < B; ++r) slot_of[r] = -1;
+        if (ctrl && (ctrl->flags & ETAI_CTRL_CROSS_STORE) && HW == (long)ctrl->store_res * ctrl->store_res) {
+            float* acc = t.place == 0 ? ctrl->store_down : t.place == 1 ? ctrl->store_mid : ctrl->store_up;
+            if (acc) {
+                a.store = acc;
+                for (int i = 0; i < ctrl->n_store_rows; ++i) {
+                    ETAI_CHECK(ctrl->store_row[i] >= 0 && ctrl->store_row[i] < B, ETAI_ERR_ARG, "store row out of range");
+                    slot_of[ctrl->store_row[i]] = i;
+                }
+            }
+        }
+        bool used[ETAI_MAX_ROWS] = {false};
+        int ng = 0;
+        if (ctrl && (ctrl->flags & ETAI_CTRL_CROSS_EDIT)) {
+            a.mapper = ctrl->mapper; a.blend_a = ctrl->blend_a; a.equalizer = ctrl->equalizer; a.alpha_step = ctrl->alpha_step;
+            for (int p = 0; p < ctrl->n_pairs; ++p) {
+                int br = ctrl->edit_base_row[p], tr = ctrl->edit_tgt_row[p];
+                ETAI_CHECK(br >= 0 && br < B && tr >= 0 && tr < B && br != tr && !used[br] && !used[tr], ETAI_ERR_ARG,
+                           "bad cross-edit pair");
+                used[br] = used[tr] = true;
+                a.groups[ng++] = CrossGroup{br, tr, p, slot_of[br], slot_of[tr]};
+            }
+        }
+        for (int r = 0; r < B; ++r)
+            if (!used[r]) a.groups[ng++] = CrossGroup{r, -1, 0, slot_of[r], -1};
+        a.n_groups = ng;
+        cross_attention(a, s);
+    }
+    h = linear(co, M, t.o2, h, s);
+    // ---- feed forward (GEGLU) ----
+    void* n3 = lnorm(h, M, t.ln3, s);
+    void* f = linear(n3, M, t.ff1, nullptr, s, /*geglu=*/1);
+    h = linear(f, M, t.ff2, h, s);
+    return linear(h, M, t.pout, x, s);
+}
+
+void etai_unet::set_context(const void* ctx, int io_dtype, int B, cudaStream_t s) {
+    ETAI_CHECK(B >= 1 && B <= cfg.max_batch, ETAI_ERR_ARG, "set_context: batch out of range");
+    long M = (long)B * cfg.ctx_len;
+    convert(ctx, io_dtype, ctx_buf, dt, M * cfg.cross_dim, s);
+    GemmArgs a;
+    a.A = ctx_buf; a.W = kv_all.w; a.C = kv_cache;
+    a.M = M; a.N = kv_all.n; a.K = kv_all.k; a.lda = kv_all.k; a.ldc = kv_all.n;
+    gemm(a, s);
+    ctx_rows = B;
+}
+
+void etai_unet::forward(const void* latent, float t, int io_dtype, int B, const etai_attn_ctrl* ctrl, void* eps_out,
+                        cudaStream_t s) {
+    const bool planning = arena.base == nullptr;
+    if (!planning) {
+        ETAI_CHECK(B >= 1 && B <= cfg.max_batch, ETAI_ERR_ARG, "forward: batch out of range");
+        ETAI_CHECK(ctx_rows == B, ETAI_ERR_STATE, "forward: etai_unet_set_context must be called with the same batch first");
+    }
+    const int* c = cfg.block_out_channels;
+    const int temb = c[0] * 4;
+    int H = cfg.latent_hw, W = cfg.latent_hw;
+    arena.reset();
+
+    // time embedding (t is shared by all rows): all fp32, M = 1 skinny GEMMs
+    if (!planning) {
+        timestep_sincos(t, tbuf + TB_SIN, c[0], s);
+        skinny_linear(tbuf + TB_SIN, time1.w, time1.b, tbuf + TB_H1, 1, temb, c[0], 1, dt, s);        // silu(linear_1)
+        skinny_linear(tbuf + TB_H1, time2.w, time2.b, tbuf + TB_ST, 1, temb, temb, 1, dt, s);          // silu(temb)
+        skinny_linear(tbuf + TB_ST, temb_all.w, temb_all.b, tbuf + TB_PROJ, 1, temb_all.n, temb, 0, dt, s);
+    }
+
+    void* x = arena.alloc((size_t)B * H * W * 4 * esz);
+    if (!planning) nchw_to_nhwc(latent, io_dtype, x, dt, B, 4, (long)H * W, s);
+    void* h = conv3x3(x, B, H, W, conv_in, 1, nullptr, nullptr, s);
+
+    struct Skip { void* p; int C; };
+    std::vector<Skip> skips;
+    skips.push_back({h, c[0]});
+    for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 2; ++j) {
+            h = resnet(h, B, H, W, down_res[i][j], ctrl, false, s);
+            if (i < 3) h = transformer(h, B, H, W, down_tf[i][j], ctrl, s);
+            skips.push_back({h, c[i]});
+        }
+        if (i < 3) {
+            h = conv3x3(h, B, H, W, down_samp[i], 2, nullptr, nullptr, s);
+            H /= 2; W /= 2;
+            skips.push_back({h, c[i]});
+        }
+    }
+    h = resnet(h, B, H, W, mid_res[0], ctrl, false, s);
+    h = transformer(h, B, H, W, mid_tf, ctrl, s);
+    h = resnet(h, B, H, W, mid_res[1], ctrl, false, s);
+    int hc = c[3];
+    for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < 3; ++j) {
+            Skip sk = skips.back();
+            skips.pop_back();
+            long rows = (long)B * H * W;
+            void* cat = arena.alloc((size_t)rows * (hc + sk.C) * esz);
+            if (!planning) concat_channels(h, hc, sk.p, sk.C, cat, rows, dt, s);
+            const Res& r = up_res[i][j];
+            ETAI_CHECK(r.cin == hc + sk.C, ETAI_ERR_STATE, "skip bookkeeping mismatch");
+            h = resnet(cat, B, H, W, r, ctrl, i == 1 && j == 1, s);
+            hc = r.cout;
+            if (i > 0) h = transformer(h, B, H, W, up_tf[i][j], ctrl, s);
+        }
+        if (i < 3) {
+            void* up = arena.alloc((size_t)B * H * W * 4 * hc * esz);
+            if (!planning) upsample2x(h, up, B, H, W, hc, dt, s);
+            H *= 2; W *= 2;
+            h = conv3x3(up, B, H, W, up_samp[i], 1, nullptr, nullptr, s);
+        }
+    }
+    void* a = gnorm(h, B, (long)H * W, norm_out, 1e-5f, true, s);
+    void* o = conv3x3(a, B, H, W, conv_out, 1, nullptr, nullptr, s);
+    if (!planning) nhwc_to_nchw(o, dt, eps_out, io_dtype, B, 4, (long)H * W, s);
+}
+
+void etai_unet::plan_workspace() {
+    // dry run with a null arena to size it for max_batch
+    arena.base = nullptr;
+    arena.cap = 0;
+    arena.peak = 0;
+    forward(nullptr, 0.f, ETAI_F32, cfg.max_batch, nullptr, nullptr, 0);
+    size_t need = arena.peak + 4096;
+    void* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, need));
+    arena.base = (char*)p;
+    arena.cap = need;
+    arena.reset();
+    workspace_bytes = need;
+    long ctx_m = (long)cfg.max_batch * cfg.ctx_len;
+    CUDA_CHECK(cudaMalloc(&kv_cache, (size_t)ctx_m * kv_total * esz));
+    CUDA_CHECK(cudaMalloc(&ctx_buf, (size_t)ctx_m * cfg.cross_dim * esz));
+    CUDA_CHECK(cudaMalloc((void**)&tbuf, (size_t)(TB_PROJ + temb_total + 64) * sizeof(float)));
+    size_t gws = groupnorm_workspace_bytes(cfg.max_batch, 0, 0, 32);
+    CUDA_CHECK(cudaMalloc(&gn_ws, gws));
+    // im2col scratch for the stride-2 convs on the tcgen05 path: largest is B*32*32 x 9*c0
+    tc_ws_bytes = 0;
+    if (tc) {
+        const int* c = cfg.block_out_channels;
+        long hw = (long)cfg.latent_hw * cfg.latent_hw / 4;
+        size_t m = 0;
+        for (int i = 0; i < 3; ++i) {
+            size_t b = (size_t)cfg.max_batch * hw * 9 * c[i] * esz;
+            if (b > m) m = b;
+            hw /= 4;
+        }
+        tc_ws_bytes = m;
+        CUDA_CHECK(cudaMalloc(&tc_ws, tc_ws_bytes));
+    }
+    workspace_bytes += (size_t)ctx_m * (kv_total + cfg.cross_dim) * esz + gws + tc_ws_bytes;
+}
+
+// -------------------------------------------------------------------------------------------------
+// C ABI
+// -------------------------------------------------------------------------------------------------
+namespace etai {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& m) { g_last_error = m; }
+}  // namespace etai
+
+#define ETAI_API_BEGIN try {
+#define ETAI_API_END                                        \
+    }                                                       \
+    catch (const etai::Error& e) {                          \
+        etai::set_last_error(e.what());                     \
+        return e.code;                                      \
+    }                                                       \
+    catch (const std::exception& e) {                       \
+        etai::set_last_error(e.what());                     \
+        return ETAI_ERR_STATE;                              \
+    }                                                       \
+    return ETAI_OK;
+
+extern "C" {
+
+int etai_abi_version(void) { return ETAI_ABI_VERSION; }
+const char* etai_last_error(void) { return etai::g_last_error.c_str(); }
+
+int etai_unet_create(etai_unet** out, const etai_unet_cfg* cfg, const etai_tensor* weights, int32_t n_weights,
+                     int32_t device) {
+    ETAI_API_BEGIN
+    ETAI_CHECK(out && cfg && weights && n_weights > 0, ETAI_ERR_ARG, "create: null argument");
+    ETAI_CHECK(cfg->dtype == ETAI_F32 || cfg->dtype == ETAI_F16 || cfg->dtype == ETAI_BF16, ETAI_ERR_ARG, "create: dtype");
+    ETAI_CHECK(cfg->max_batch >= 1 && cfg->max_batch <= ETAI_MAX_ROWS, ETAI_ERR_ARG, "create: max_batch in [1,64]");
+    ETAI_CHECK(cfg->heads >= 1 && cfg->ctx_len >= 1 && cfg->ctx_len <= 80, ETAI_ERR_ARG, "create: heads/ctx_len");
+    ETAI_CHECK(cfg->latent_hw >= 8 && cfg->latent_hw % 8 == 0, ETAI_ERR_ARG, "create: latent_hw must be a multiple of 8");
+    for (int i = 0; i < 4; ++i)
+        ETAI_CHECK(cfg->block_out_channels[i] % (8 * cfg->heads) == 0 && cfg->block_out_channels[i] % 32 == 0,
+                   ETAI_ERR_ARG, "create: channels must be multiples of 32 and of 8*heads");
+    int ndev = 0;
+    CUDA_CHECK(cudaGetDeviceCount(&ndev));
+    ETAI_CHECK(device >= 0 && device < ndev, ETAI_ERR_ARG, "create: no such CUDA device");
+    CUDA_CHECK(cudaSetDevice(device));
+    etai_unet* h = new etai_unet();
+    try {
+        h->cfg = *cfg;
+        h->device = device;
+        h->dt = cfg->dtype;
+        h->esz = dtype_size(cfg->dtype);
+        h->tc = cfg->dtype != ETAI_F32 && cfg->math_mode == ETAI_MATH_AUTO;
+        h->build(weights, n_weights);
+        h->plan_workspace();
+    } catch (...) {
+        etai_unet_destroy(h);
+        throw;
+    }
+    *out = h;
+    ETAI_API_END
+}
+
+int etai_unet_destroy(etai_unet* h) {
+    if (!h) return ETAI_OK;
+    cudaSetDevice(h->device);
+    for (void* p : h->owned) cudaFree(p);
+    if (h->arena.base) cudaFree(h->arena.base);
+    if (h->kv_cache) cudaFree(h->kv_cache);
+    if (h->ctx_buf) cudaFree(h->ctx_buf);
+    if (h->tbuf) cudaFree(h->tbuf);
+    if (h->gn_ws) cudaFree(h->gn_ws);
+    if (h->tc_ws) cudaFree(h->tc_ws);
+    if (h->stage) cudaFree(h->stage);
+    delete h;
+    return ETAI_OK;
+}
+
+int64_t etai_unet_device_bytes(const etai_unet* h) { return h ? (int64_t)(h->weight_bytes + h->workspace_bytes) : 0; }
+
+int etai_unet_set_context(etai_unet* h, const void* ctx, int32_t io_dtype, int32_t B, void* stream) {
+    ETAI_API_BEGIN
+    ETAI_CHECK(h && ctx, ETAI_ERR_ARG, "set_context: null argument");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    h->set_context(ctx, io_dtype, B, (cudaStream_t)stream);
+    ETAI_API_END
+}
+
+int etai_unet_forward(etai_unet* h, const void* latent, float t, int32_t io_dtype, int32_t B,
+                      const etai_attn_ctrl* ctrl, void* eps_out, void* stream) {
+    ETAI_API_BEGIN
+    ETAI_CHECK(h && latent && eps_out, ETAI_ERR_ARG, "forward: null argument");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    if (ctrl) {
+        if (ctrl->flags & ETAI_CTRL_SELF_REMAP)
+            ETAI_CHECK(ctrl->self_q_row && ctrl->self_k_row && ctrl->self_v_row, ETAI_ERR_ARG, "ctrl: self remap arrays");
+        if (ctrl->flags & ETAI_CTRL_CROSS_EDIT)
+            ETAI_CHECK(ctrl->n_pairs >= 1 && ctrl->n_pairs <= ETAI_MAX_PAIRS && ctrl->edit_base_row && ctrl->edit_tgt_row &&
+                           ctrl->mapper && ctrl->blend_a && ctrl->equalizer && ctrl->alpha_step,
+                       ETAI_ERR_ARG, "ctrl: cross edit tables");
+        if (ctrl->flags & ETAI_CTRL_CROSS_STORE)
+            ETAI_CHECK(ctrl->store_res > 0 && ctrl->n_store_rows >= 1 && ctrl->n_store_rows <= ETAI_MAX_ROWS && ctrl->store_row,
+                       ETAI_ERR_ARG, "ctrl: store rows");
+    }
+    h->forward(latent, t, io_dtype, B, ctrl, eps_out, (cudaStream_t)stream);
+    ETAI_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,159 @@
+"""ORACLE tooling (test infrastructure): run the UNMODIFIED reference loop/controller code
+(/root/reference/modules/**) on CPU fp32 over the diffusers restatement in oracle/sd15.py and
+write golden fixtures to tests/golden/*.npz.
+
+Only runs in the build container (needs /root/reference).  Nothing under tests/ -m gpu, smoke()
+or bench.py reads /root/reference; they read the committed fixtures.
+
+    python oracle/run_reference.py --scenario all
+
+The process chdir()s to a scratch directory first and neuters ``os.system`` because importing
+modules/inversion/eta_inversion.py executes ``rm -rf result/pie_eta_new/*`` (eta_inversion.py:19-20).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+REPO = Path(__file__).resolve().parent.parent
+REF = Path("/root/reference")
+GOLDEN = REPO / "tests" / "golden"
+
+SRC = "a cat sitting next to a mirror"
+TGT = "a tiger sitting next to a mirror"
+PTP_REPLACE = dict(is_replace_controller=True, cross_replace_steps={"default_": .8}, self_replace_steps=.5,
+                   blend_words=[["cat"], ["tiger"]], equilizer_params={"words": ["tiger"], "values": [2]})  # test/test_edit.py:32-39
+PTP_REFINE = dict(is_replace_controller=False, prompts=[SRC, TGT], cross_replace_steps={"default_": .4},
+                  self_replace_steps=0.6, blend_words=((("cat",), ("tiger",))),
+                  equilizer_params={"words": ("tiger",), "values": (2,)})  # edit_image.py:87-98
+
+SCENARIOS = {
+    # name: (inverter kwargs, editor type, editor kwargs, edit cfg, inv_cfg)
+    "diffinv_simple_4": (dict(type="diffinv", scheduler="ddim", num_inference_steps=4), "simple", {}, None, None),
+    "etainv_ptp_replace_5": (dict(type="etainv", scheduler="ddim", num_inference_steps=5, eta=(0.0, 0.4)), "ptp", {},
+                             PTP_REPLACE, dict(edit_word_idx=(1, 1))),
+    "etainv_ptp_refine_3": (dict(type="etainv", scheduler="ddim", num_inference_steps=3,
+                                 eta=[[0.6, 0.0], [1.0, 0.7]]), "ptp", {}, PTP_REFINE, dict(edit_word_idx=(1, 1))),
+    "etainv_masactrl_6": (dict(type="etainv", scheduler="ddim", num_inference_steps=6, eta=(0.0, 0.4)), "masactrl", {},
+                          None, dict(edit_word_idx=(1, 1))),
+    "dirinv_ptp_replace_3": (dict(type="dirinv", scheduler="ddim", num_inference_steps=3), "ptp", {}, PTP_REPLACE, None),
+    "npi_simple_3": (dict(type="npi", scheduler="ddim", num_inference_steps=3), "simple", {}, None, None),
+    "diffinv_pnp_5": (dict(type="diffinv", scheduler="ddim", num_inference_steps=5), "pnp", {}, None, None),
+}
+
+
+def _setup_paths():
+    os.system = lambda *a, **k: 0  # see module docstring
+    os.chdir(tempfile.mkdtemp(prefix="etai_oracle_"))
+    sys.path[:0] = [str(REPO / "oracle" / "shim"), str(REPO), str(REF)]
+
+
+def build_model():
+    from eta_inversion_b200 import synthetic as syn
+    from oracle import sd15
+    pipe = sd15.build_pipeline(syn.random_state_dict(syn.unet_param_spec(), 0),
+                               syn.random_state_dict(syn.vae_param_spec(), 1), seed=0)
+    return pipe, syn
+
+
+def pool8(img: torch.Tensor) -> np.ndarray:
+    return torch.nn.functional.avg_pool2d(img, 8).numpy()
+
+
+def run_unet_fwd(pipe):
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn((4, 4, 64, 64), generator=g)
+    ctx = torch.randn((4, 77, 768), generator=g)
+    out = {}
+    with torch.no_grad():
+        for t in (981, 1):
+            out[f"eps_t{t}"] = pipe.unet(x, torch.tensor(t), encoder_hidden_states=ctx)["sample"].numpy()
+    np.savez_compressed(GOLDEN / "unet_fwd.npz", **out)
+    print("unet_fwd", {k: float(np.abs(v).mean()) for k, v in out.items()})
+
+
+def run_scenario(name, pipe, syn):
+    import modules  # the reference's own package
+    inv_kw, ed_type, ed_kw, cfg, inv_cfg = SCENARIOS[name]
+    inverter = modules.load_inverter(model=pipe, **inv_kw)
+    editor = modules.load_editor(inverter=inverter, type=ed_type, **ed_kw)
+    image = syn.synthetic_image(0)
+    rec = {"bwd_latents": [], "bwd_eps": [], "picks": []}
+
+    # record every backward step without touching the reference's code
+    orig_psb = inverter.predict_step_backward
+
+    def psb(*a, **k):
+        new_latent, eps = orig_psb(*a, **k)
+        rec["bwd_latents"].append(new_latent.detach().clone().numpy())
+        rec["bwd_eps"].append(eps.detach().clone().numpy())
+        return new_latent, eps
+    inverter.predict_step_backward = psb
+    if hasattr(inverter, "get_eta_variance_noise"):
+        orig_sample, orig_get = inverter.sample_variance_noise, inverter.get_eta_variance_noise
+        last = {}
+
+        def sample_vn(n, generator=None):
+            last["c"] = orig_sample(n, generator)
+            return last["c"]
+
+        def get_eta(*a, **k):
+            r = orig_get(*a, **k)
+            idx = [i for i in range(last["c"].shape[0]) if torch.equal(last["c"][i], r["variance_noise"])]
+            rec["picks"].append(idx[0])
+            return r
+        inverter.sample_variance_noise, inverter.get_eta_variance_noise = sample_vn, get_eta
+    orig_invert = inverter.invert
+    inv_box = {}
+
+    def invert(*a, **k):
+        inv_box["res"] = orig_invert(*a, **k)
+        return inv_box["res"]
+    inverter.invert = invert
+
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        res = editor.edit(image, SRC, TGT, cfg=None if cfg is None else {**cfg}, inv_cfg=inv_cfg)
+    dt = time.perf_counter() - t0
+    out = dict(
+        inv_latents=np.stack([l.numpy() for l in inv_box["res"]["latents"]]),
+        inv_eps=np.stack([e.numpy() for e in inv_box["res"]["noise_preds"]]),
+        bwd_latents=np.stack(rec["bwd_latents"]), bwd_eps=np.stack(rec["bwd_eps"]),
+        latent=res["latent"].numpy(), latent_inv=res["latent_inv"].numpy(),
+        image_pool8=pool8(res["image"]), image_inv_pool8=pool8(res["image_inv"]),
+        image_mean=np.array([res["image"].mean().item(), res["image_inv"].mean().item()]),
+        seconds=np.array(dt),
+    )
+    if rec["picks"]:
+        out["picks"] = np.array(rec["picks"], dtype=np.int64)
+    if getattr(inverter, "attn_maps_forward", None):
+        out["fwd_mean_map"] = inverter.attn_maps_forward["mean"][inv_cfg["edit_word_idx"][0]].numpy()
+    np.savez_compressed(GOLDEN / f"{name}.npz", **out)
+    print(name, f"{dt:.1f}s", {k: v.shape for k, v in out.items()}, "picks", rec["picks"])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scenario", default="all")
+    args = ap.parse_args()
+    _setup_paths()
+    torch.set_num_threads(os.cpu_count())
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    pipe, syn = build_model()
+    names = ["unet_fwd"] + list(SCENARIOS) if args.scenario == "all" else args.scenario.split(",")
+    for n in names:
+        if n == "unet_fwd":
+            run_unet_fwd(pipe)
+        else:
+            run_scenario(n, pipe, syn)
+
+
+if __name__ == "__main__":
+    main()

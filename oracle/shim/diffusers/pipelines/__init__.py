@@ -1,0 +1,2 @@
+"""ORACLE shim (test infrastructure): re-exports oracle.sd15 under the module paths the reference imports."""
+from . import stable_diffusion  # noqa: F401

@@ -1,0 +1,2 @@
+"""ORACLE shim (test infrastructure): re-exports oracle.sd15 under the module paths the reference imports."""
+from oracle.sd15 import DDIMScheduler, DDIMSchedulerOutput  # noqa: F401
