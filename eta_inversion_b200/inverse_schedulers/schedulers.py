@@ -1,0 +1,178 @@
+"""DDIM schedulers of the hot path.  Host side = constants and timestep bookkeeping; the arithmetic of every step is
+the fused CUDA kernel ``etai_cfg_ddim_step`` (eta_inversion_b200/csrc/elementwise.cu).
+
+Interfaces mirrored:
+  DiffusionInverseScheduler / DDIMInverseScheduler   modules/inverse_schedulers/diffusion_inverse_scheduler.py:5-29,
+                                                     modules/inverse_schedulers/scheduling_ddim_inverse.py:9-143
+  DDIMScheduler (the diffusers class the reference instantiates at diffusion_inversion.py:146; used through
+                 from_config / config / set_timesteps / timesteps / alphas_cumprod / final_alpha_cumprod /
+                 step(eps,t,x,eta=,variance_noise=).prev_sample / _get_variance)      SURVEY.md Appendix B
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+from typing import Optional
+
+import numpy as np
+import torch
+
+from .. import engine as E
+
+
+class FrozenConfig(dict):
+    """dict with attribute access; ``{**scheduler.config}`` works like diffusers' FrozenDict."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+DDIMSchedulerOutput = namedtuple("DDIMSchedulerOutput", ("prev_sample", "pred_original_sample"))
+
+
+def _f(v) -> float:
+    return float(v.item() if torch.is_tensor(v) else v)
+
+
+class DDIMScheduler:
+    """Backward (denoising) DDIM scheduler; same constructor defaults as diffusers 0.21.1."""
+
+    _defaults = dict(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                     trained_betas=None, clip_sample=True, set_alpha_to_one=True, steps_offset=0,
+                     prediction_type="epsilon", thresholding=False, dynamic_thresholding_ratio=0.995,
+                     clip_sample_range=1.0, sample_max_value=1.0, timestep_spacing="leading",
+                     rescale_betas_zero_snr=False)
+
+    def __init__(self, **kwargs):
+        cfg = {**self._defaults, **{k: v for k, v in kwargs.items() if k in self._defaults}}
+        self.config = FrozenConfig(cfg)
+        n = cfg["num_train_timesteps"]
+        if cfg["beta_schedule"] == "linear":
+            betas = torch.linspace(cfg["beta_start"], cfg["beta_end"], n, dtype=torch.float32)
+        elif cfg["beta_schedule"] == "scaled_linear":
+            betas = torch.linspace(cfg["beta_start"] ** 0.5, cfg["beta_end"] ** 0.5, n, dtype=torch.float32) ** 2
+        else:
+            raise NotImplementedError(f"beta_schedule {cfg['beta_schedule']}")
+        if cfg["prediction_type"] != "epsilon" or cfg["thresholding"] or cfg["timestep_spacing"] != "leading":
+            raise NotImplementedError("only epsilon prediction / leading spacing (the SD-1.x setting) is built")
+        self.betas = betas
+        self.alphas = 1.0 - betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)  # fp32 on the host like the reference
+        self.final_alpha_cumprod = torch.tensor(1.0) if cfg["set_alpha_to_one"] else self.alphas_cumprod[0]
+        self.init_noise_sigma = 1.0
+        self.num_inference_steps = None
+        self.timesteps = torch.from_numpy(np.arange(0, n)[::-1].copy().astype(np.int64))
+
+    @classmethod
+    def from_config(cls, config, **kwargs):
+        return cls(**{**dict(config), **kwargs})
+
+    def set_timesteps(self, num_inference_steps: int, device=None) -> None:
+        self.num_inference_steps = num_inference_steps
+        ratio = self.config.num_train_timesteps // num_inference_steps
+        ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64)
+        self.timesteps = torch.from_numpy(ts + self.config.steps_offset)  # CPU int64, descending
+
+    # ---- constants -------------------------------------------------------------------------------
+    def alpha(self, t: int) -> float:
+        t = int(t)
+        return _f(self.alphas_cumprod[t]) if t >= 0 else _f(self.final_alpha_cumprod)
+
+    def prev_timestep(self, t) -> int:
+        return int(t) - self.config.num_train_timesteps // self.num_inference_steps
+
+    def _get_variance(self, timestep, prev_timestep):
+        a_t = self.alphas_cumprod[int(timestep)]
+        a_p = self.alphas_cumprod[int(prev_timestep)] if prev_timestep >= 0 else self.final_alpha_cumprod
+        return ((1 - a_p) / (1 - a_t)) * (1 - a_t / a_p)
+
+    # ---- fused step -----------------------------------------------------------------------------
+    def fused_step(self, eps_raw: torch.Tensor, timestep, sample: torch.Tensor, guidance: Optional[float] = None,
+                   eta: float = 0.0, eta_map=None, noise_cand=None, losses=None, pin_src=None):
+        """CFG + DDIM denoise step in one launch.  Returns (prev_sample, eps_cfg)."""
+        if self.config.clip_sample:
+            raise NotImplementedError("clip_sample=True is not used on this path (diffusion_inversion.py:132-136)")
+        t, p = int(timestep), self.prev_timestep(timestep)
+        return E.cfg_ddim_step(eps_raw, sample, self.alpha(t), self.alpha(p), guidance, eta,
+                               _f(self._get_variance(t, p)), eta_map, noise_cand, losses, pin_src, want_eps=True)
+
+    def step(self, model_output, timestep, sample, eta=0.0, use_clipped_model_output=False, generator=None,
+             variance_noise=None, return_dict=True):
+        """diffusers call shape: eps is already CFG-combined.  eta may be a float or a tensor map."""
+        eta_map, eta_s = None, eta
+        if torch.is_tensor(eta) or hasattr(eta, "eta"):
+            m = getattr(eta, "eta", eta)
+            eta_map = torch.broadcast_to(m.float(), (1,) + tuple(sample.shape[1:])).contiguous()  # shared by all rows
+            eta_s = 1.0
+        if float(eta_s) > 0 and variance_noise is None:
+            variance_noise = torch.randn(sample.shape[1:], generator=generator, device=sample.device, dtype=torch.float32)[None]
+        cand = None if variance_noise is None else variance_noise.reshape(1, -1).float().contiguous()
+        prev, _ = self.fused_step(model_output.float().contiguous(), timestep, sample.float().contiguous(), None,
+                                  float(eta_s), eta_map, cand)
+        return DDIMSchedulerOutput(prev.to(sample.dtype), None)
+
+
+class DiffusionInverseScheduler:
+    def set_timesteps(self, num_inference_steps: int) -> None:
+        raise NotImplementedError
+
+    def step(self, noise_pred, t, latent, *args, **kwargs):
+        raise NotImplementedError
+
+
+class DDIMInverseScheduler(DiffusionInverseScheduler):
+    """Inverse DDIM: walks z0 -> zT.  Modes as in scheduling_ddim_inverse.py:127-138."""
+
+    Output = namedtuple("DDIMInverseSchedulerOutput", ("prev_sample",))
+
+    def __init__(self, scheduler: DDIMScheduler, inv_steps: str = "sameshift") -> None:
+        self.scheduler = scheduler
+        self.is_backward = False
+        self.inv_steps = inv_steps
+
+    @staticmethod
+    def from_scheduler(scheduler: DDIMScheduler, inv_steps: str = "sameshift", **kwargs) -> "DDIMInverseScheduler":
+        return DDIMInverseScheduler(DDIMScheduler.from_config({**scheduler.config, **kwargs}), inv_steps=inv_steps)
+
+    def set_timesteps(self, num_inference_steps: int) -> None:
+        self.scheduler.set_timesteps(num_inference_steps)
+
+    @property
+    def timesteps(self):
+        steps = reversed(self.scheduler.timesteps)  # torch.Tensor.__reversed__ == flip(0)
+        if self.scheduler.config.steps_offset != 0:
+            assert steps[0] == 1
+        if self.inv_steps == "shiftshift":
+            steps = [self.get_timestep(s, -1) for s in steps]
+        return steps
+
+    def get_timestep(self, timestep, offset: int):
+        return timestep + offset * (self.scheduler.config.num_train_timesteps // self.scheduler.num_inference_steps)
+
+    def _endpoints(self, t):
+        if not self.is_backward:
+            if self.inv_steps == "sameshift":
+                return self.get_timestep(t, -1), t
+            if self.inv_steps in ("samesame", "shiftshift"):
+                return t, self.get_timestep(t, +1)
+            raise Exception(self.inv_steps)
+        return t, self.get_timestep(t, -1)
+
+    def _alphas(self, t_from, t_to):
+        t_from, t_to = min(int(t_from), 999), min(int(t_to), 999)
+        return self.scheduler.alpha(t_from), self.scheduler.alpha(t_to)
+
+    def ddim_step(self, sample, model_output, timestep_from, timestep_to):
+        a_f, a_t = self._alphas(timestep_from, timestep_to)
+        return E.cfg_ddim_step(model_output.float().contiguous(), sample.float().contiguous(), a_f, a_t).to(sample.dtype)
+
+    def fused_step(self, eps_raw, t, latent, guidance: Optional[float] = None):
+        """CFG + inverse DDIM step in one launch. Returns (next_latent, eps_cfg)."""
+        a_f, a_t = self._alphas(*self._endpoints(t))
+        return E.cfg_ddim_step(eps_raw, latent, a_f, a_t, guidance, want_eps=True)
+
+    def step(self, noise_pred, t, latent):
+        t_from, t_to = self._endpoints(t)
+        return DDIMInverseScheduler.Output(self.ddim_step(latent, noise_pred, t_from, t_to))

@@ -1,0 +1,204 @@
+"""Eta inversion (reference: modules/inversion/eta_inversion.py:36-403; ECCV 2024 "Eta Inversion").
+
+Loop A (inversion): DDIM inversion at CFG scale `guidance_scale_fwd` while the cross-attention maps of the source
+prompt are accumulated (ControllerAttentionStorePerStep) -> per-word 64x64 maps, averaged over steps.
+Loop B (edit): DDIM denoising with eta(t) > 0 only inside the thresholded map of the edited word; the injected
+variance noise is the best of `noise_sample_count` candidates (closest to the noise that would reproduce the
+inversion trajectory); the source row is pinned to the stored trajectory.
+
+Per edit step the device work is: 1 UNet forward (B=4) + `etai_eta_noise_losses` + `etai_cfg_ddim_step`
+(CFG, eta map, on-device argmin pick, noise injection, source pin) -- no host sync (the reference does
+``argmin().item()`` per step, eta_inversion.py:363).  Noise candidates are pre-generated for the whole loop from the
+same seeded CPU generator stream the reference consumes on CPU (RNG quirk).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .. import engine as E
+from ..editing.ptp_editor import PromptToPromptControllerAttentionStore
+from .diffusion_inversion import DiffusionInversion
+
+
+class ControllerAttentionStorePerStep(PromptToPromptControllerAttentionStore):
+    def __init__(self, model, prompt, res, from_where, callback) -> None:
+        super().__init__(model, max_size=res)
+        self.callback, self.prompt, self.res, self.from_where = callback, prompt, res, from_where
+
+    def end_step(self, latent, noise_pred=None, t=None):
+        words = self.prompt.split(" ")
+        # one token per word; a repeated word resolves to its FIRST occurrence (ptp_editor.py:72, list.index)
+        idx = [words.index(w) + 1 for w in words]
+        maps = self.get_attention_maps(idx, res=self.res, from_where=self.from_where, resize=64)
+        self.callback([maps[i] for i in range(len(words))], t)  # per word [1,64,64]
+        return super().end_step(latent, noise_pred, t)
+
+
+def make_eta_schedule(eta, num_train_steps: int = 1000) -> np.ndarray:
+    """etas[t] for t in [0,1000): scalar | (start,end) linear | ((x1,y1),(x2,y2)[,p]) clipped power law over t/1000
+    (eta_inversion.py:52-58,115-137); no eval()."""
+    if not isinstance(eta, (tuple, list)):
+        eta = eta, eta
+    if len(eta) == 3 or isinstance(eta[0], (tuple, list)):
+        (x1, y1), (x2, y2) = eta[0], eta[1]
+        p = eta[2] if len(eta) == 3 else 1
+        a = (y2 - y1) / (x2 - x1) ** p
+        ts = np.linspace(0, 1, num_train_steps)
+        etas = a * (np.clip(ts, x1, x2) - x1) ** p + y1
+    else:
+        etas = np.linspace(eta[0], eta[1], num_train_steps)
+    return np.clip(etas, 0, None)
+
+
+class EtaInversion(DiffusionInversion):
+    def __init__(self, model, scheduler: Optional[str] = None, num_inference_steps: Optional[int] = None,
+                 guidance_scale_bwd: Optional[float] = None, guidance_scale_fwd: Optional[float] = None,
+                 verbose: bool = False, eta=(0.0, 0.4), noise_sample_count: int = 10, seed: int = 0,
+                 eta_start: Optional[float] = None, eta_end: Optional[float] = None, use_mask=True,
+                 mask_mode_cfg=None) -> None:
+        if use_mask:
+            dft = dict(attn_from_where=["up", "down"], attn_res=16, mask_dirinv=None, mask_eta="fwd_mean", pow=None,
+                       target_dirinv=None, thres=0.2)
+            mask_mode_cfg = {**dft, **(mask_mode_cfg or {})}
+        else:
+            mask_mode_cfg = None
+        self.mask_mode_cfg = mask_mode_cfg
+        if isinstance(guidance_scale_fwd, (tuple, list)):
+            assert len(guidance_scale_fwd) == 2
+            guidance_scale_fwd = np.linspace(guidance_scale_fwd[0], guidance_scale_fwd[1], 1000)
+        super().__init__(model, scheduler, num_inference_steps, guidance_scale_bwd, guidance_scale_fwd, verbose)
+        if eta_start is not None:
+            assert eta_end is not None
+            eta = (eta_start, eta_end)
+        self.etas = make_eta_schedule(eta)
+        self.attn_maps_forward: Dict[Any, Any] = {}
+        self.noise_sample_count = noise_sample_count
+        self.seed = seed if seed >= 0 else None
+        self.noise_provider = None  # optional callable(step_index) -> [K,1,4,64,64]; default = seeded CPU stream
+
+    # ---- noise -----------------------------------------------------------------------------------
+    def sample_variance_noise(self, n: int, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        hw = self.unet.latent_hw
+        return torch.randn((n, 1, 4, hw, hw), generator=generator).to(self.model.device)
+
+    def _noise_for_loop(self, steps: int) -> torch.Tensor:
+        if self.noise_provider is not None:
+            return torch.stack([self.noise_provider(i) for i in range(steps)]).to(self.model.device, torch.float32)
+        g = torch.Generator()
+        if self.seed is not None:
+            g.manual_seed(self.seed)
+        hw = self.unet.latent_hw
+        # one draw for the whole loop == the reference's per-step draws from one generator (numel multiple of 16)
+        return torch.randn((steps, self.noise_sample_count, 1, 4, hw, hw), generator=g).to(self.model.device)
+
+    # ---- masks -----------------------------------------------------------------------------------
+    def get_mask(self, key, mask, t, edit_word_idx):
+        if self.mask_mode_cfg is None:
+            return None
+        res, from_where, mode = self.mask_mode_cfg["attn_res"], self.mask_mode_cfg["attn_from_where"], self.mask_mode_cfg[key]
+        if mode == "gt":
+            pass
+        elif mode == "fwd":
+            mask = self.attn_maps_forward[t.item()][edit_word_idx[0]]
+        elif mode == "fwd_mean":
+            mask = self.attn_maps_forward["mean"][edit_word_idx[0]]
+        elif mode in ("bwd_source", "bwd_target", "bwd_source_target"):
+            ms = self.controller.get_attention_map(mask_idx=edit_word_idx[0], res=res, from_where=from_where, prompt_idx=0, num_prompts=2, resize=64)
+            mt = self.controller.get_attention_map(mask_idx=edit_word_idx[1], res=res, from_where=from_where, prompt_idx=1, num_prompts=2, resize=64)
+            mask = ms if mode == "bwd_source" else mt if mode == "bwd_target" else torch.maximum(ms, mt)
+        elif mode is None:
+            return None
+        else:
+            assert False
+        if self.mask_mode_cfg["thres"] is not None:
+            mask = (mask > self.mask_mode_cfg["thres"]).to(mask.dtype)
+        if self.mask_mode_cfg["pow"] is not None:
+            mask = torch.pow(mask, self.mask_mode_cfg["pow"])
+        return mask
+
+    # ---- UNet call: always the full [uncond, cond] batch (eta_inversion.py:319-328) ---------------
+    def _unet_eps(self, latent, t, context, guidance_scale, is_fwd: bool = False):
+        latent_input = torch.cat([latent] * 2) if latent.shape[0] != context.shape[0] else latent
+        if is_fwd:
+            guidance_scale = self.guidance_scale_fwd
+        if isinstance(guidance_scale, (tuple, list, dict, np.ndarray)):
+            guidance_scale = guidance_scale[t.item()]
+        return self._forward_unet(latent_input, t, context), float(guidance_scale)
+
+    # ---- loop B step -----------------------------------------------------------------------------
+    def predict_step_backward(self, latent, t, context, guidance_scale_bwd: Optional[float] = None,
+                              source_latent_prev=None, generator=None, mask=None, edit_word_idx=None,
+                              noise_cand: Optional[torch.Tensor] = None):
+        guidance_scale_bwd = guidance_scale_bwd or self.guidance_scale_bwd
+        latent = self.controller.begin_step(latent=latent, t=t)
+        latent = latent.float().contiguous()
+        eps_raw, g = self._unet_eps(latent, t, context, guidance_scale_bwd)
+        if noise_cand is None:
+            noise_cand = self.sample_variance_noise(self.noise_sample_count, generator)
+        cand = noise_cand.reshape(noise_cand.shape[0], -1).float().contiguous()
+        sch = self.scheduler_bwd
+        ti, pi = int(t), sch.prev_timestep(t)
+        a_t, a_p, var = sch.alpha(ti), sch.alpha(pi), float(sch._get_variance(ti, pi))
+        eta = float(self.etas[ti])
+        src_prev = source_latent_prev.float().contiguous()
+        n = latent.shape[0]
+        losses = None
+        if eta > 0 and cand.shape[0] > 1:
+            losses, _ = E.eta_noise_losses(eps_raw, latent, src_prev, a_t, a_p, g, eta, var, cand)
+        eta_map = None
+        delta_mask = None
+        if self.mask_mode_cfg is not None:
+            m = self.get_mask("mask_eta", mask, t, edit_word_idx)
+            delta_mask = self.get_mask("mask_dirinv", mask, t, edit_word_idx)
+            if m is not None:
+                eta_map = torch.broadcast_to(m.float(), (1,) + tuple(latent.shape[1:])).contiguous()
+        leak = self.mask_mode_cfg["target_dirinv"] if self.mask_mode_cfg is not None else None
+        if leak is None:
+            new_latent, noise_pred = E.cfg_ddim_step(eps_raw, latent, a_t, a_p, g, eta, var, eta_map, cand, losses,
+                                                     pin_src=src_prev, want_eps=True)
+        else:  # rarely used variant (eta_inversion.py:251-256): leak the source delta into the target rows
+            new_latent, noise_pred = E.cfg_ddim_step(eps_raw, latent, a_t, a_p, g, eta, var, eta_map, cand, losses,
+                                                     want_eps=True)
+            delta = src_prev[:1] - new_latent[:1]
+            new_latent[:1] = new_latent[:1] + delta
+            if delta_mask is not None:
+                delta = (1 - delta_mask) * delta
+            new_latent[1:] = new_latent[1:] + leak * delta
+        new_latent = self.controller.end_step(latent=new_latent, noise_pred=noise_pred, t=t)
+        return new_latent, noise_pred
+
+    def diffusion_backward(self, latent, context, inv_result: Dict[str, Any]) -> torch.Tensor:
+        inv_cfg = inv_result["inv_cfg"] or {}
+        mask = inv_cfg.get("mask", None)
+        edit_word_idx = inv_cfg.get("edit_word_idx", None)
+        if mask is not None:
+            mask = F.interpolate(mask[None, None].float(), (64, 64), mode="bilinear")[0].to(self.model.device)
+        steps = self.scheduler_bwd.timesteps
+        noise = self._noise_for_loop(len(steps))
+        for i, t in enumerate(self.pbar(steps, desc="backward")):
+            latent, noise_pred = self.predict_step_backward(
+                latent, t, context, source_latent_prev=inv_result["latents"][-(i + 2)], mask=mask,
+                edit_word_idx=edit_word_idx, noise_cand=noise[i])
+        return latent
+
+    # ---- loop A ----------------------------------------------------------------------------------
+    def invert(self, image, prompt: Optional[str] = None, context: Optional[torch.Tensor] = None,
+               guidance_scale_fwd: Optional[float] = None, inv_cfg: Optional[Dict[str, Any]] = None) -> Dict[str, Any]:
+        if self.mask_mode_cfg is None:
+            return super().invert(image, prompt, context, guidance_scale_fwd, inv_cfg=inv_cfg)
+        if inv_cfg["edit_word_idx"][0] is None or inv_cfg["edit_word_idx"][1] is None:
+            return None
+        self.attn_maps_forward = {}
+        store = ControllerAttentionStorePerStep(
+            self.model, prompt, res=self.mask_mode_cfg["attn_res"], from_where=self.mask_mode_cfg["attn_from_where"],
+            callback=(lambda attn, t: self.attn_maps_forward.update({t.item(): attn})))
+        with self.use_controller(store):
+            fwd_result = super().invert(image, prompt, context, guidance_scale_fwd, inv_cfg=inv_cfg)
+        per_step = list(self.attn_maps_forward.values())
+        self.attn_maps_forward["mean"] = [torch.mean(torch.stack([a[w] for a in per_step]), dim=0)
+                                          for w in range(len(per_step[0]))]
+        return fwd_result

@@ -1,0 +1,145 @@
+"""Model container, pre/post-processing and loader; mirrors modules/models/__init__.py of the reference
+(StablePreprocess :11-76, StablePostProc :79-101, load_diffusion_model :104-138).
+
+The pipeline object exposes exactly what the reference's loops touch:
+``.unet(sample, t, encoder_hidden_states=)["sample"]`` (the native engine), ``.unet.dtype``, ``.vae.encode/.decode``,
+``.vae.dtype``, ``.tokenizer``, ``.text_encoder(ids)[0]``, ``.scheduler``, ``.device``.
+"""
+from __future__ import annotations
+
+import zlib
+from pathlib import Path
+from types import SimpleNamespace
+from typing import Any, Dict, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import synthetic
+from .engine import UNetEngine
+from .inverse_schedulers import DDIMScheduler
+from .vae import AutoencoderKL, make_text_encoder
+
+
+class StablePreprocess:
+    """Image file / uint8 array -> [1,3,size,size] float tensor in [-1,1] on `device`."""
+
+    def __init__(self, device: str, size: int = 512, return_np: bool = False, center_crop: bool = False,
+                 pil_resize: bool = False) -> None:
+        self.device, self.size, self.return_np = device, size, return_np
+        self.center_crop, self.pil_resize = center_crop, pil_resize
+
+    def __call__(self, image: Union[str, Path, np.ndarray]):
+        import cv2
+        if isinstance(image, (str, Path)):
+            image = cv2.cvtColor(cv2.imread(str(image)), cv2.COLOR_BGR2RGB)
+        if self.center_crop:
+            h, w = image.shape[:2]
+            if w > h:
+                lo = (w - h) // 2
+                hi = w - h - lo
+                if hi > 0:
+                    image = image[:, lo:-hi]
+            else:
+                lo = (h - w) // 2
+                hi = h - w - lo
+                if hi > 0:
+                    image = image[lo:-hi]
+        if self.pil_resize:
+            from PIL import Image
+            image = np.array(Image.fromarray(image).resize((self.size, self.size)))
+        else:
+            image = cv2.resize(image, (self.size, self.size))
+        image_pt = (torch.from_numpy(image).float() / 127.5 - 1).permute(2, 0, 1).unsqueeze(0).to(self.device)
+        return (image_pt, image) if self.return_np else image_pt
+
+
+class StablePostProc:
+    """VAE output -> uint8 HWC array of the first image."""
+
+    def __call__(self, image: torch.Tensor) -> np.ndarray:
+        image = (image.float() / 2 + 0.5).clamp(0, 1)
+        image = image.cpu().permute(0, 2, 3, 1).numpy()
+        return (image * 255).astype(np.uint8)[0]
+
+
+class SyntheticTokenizer:
+    """Deterministic whitespace tokenizer standing in for CLIPTokenizer (no vocab files on the box):
+    one id per word (crc32), BOS 49406, EOS/pad 49407, so ``get_word_inds`` == word index + 1."""
+
+    bos, eos = 49406, 49407
+    model_max_length = 77
+
+    def __init__(self):
+        self._words: Dict[int, str] = {}
+
+    def _id(self, w: str) -> int:
+        i = zlib.crc32(w.encode()) % 49000 + 1
+        self._words[i] = w
+        return i
+
+    def encode(self, text: str):
+        return [self.bos] + [self._id(w) for w in text.split(" ") if w != ""] + [self.eos]
+
+    def decode(self, ids) -> str:
+        names = {self.bos: "<|startoftext|>", self.eos: "<|endoftext|>"}
+        return " ".join(names.get(int(i), self._words.get(int(i), "?")) for i in ids)
+
+    def __call__(self, texts, padding="max_length", max_length=77, truncation=True, return_tensors="pt"):
+        if isinstance(texts, str):
+            texts = [texts]
+        rows = []
+        for t in texts:
+            ids = self.encode(t)[:max_length]
+            if len(ids) == max_length:
+                ids[-1] = self.eos
+            rows.append(ids + [self.eos] * (max_length - len(ids)))
+        return SimpleNamespace(input_ids=torch.tensor(rows, dtype=torch.int64))
+
+
+class EtaiPipeline:
+    """Stand-in for diffusers' StableDiffusionPipeline with the native UNet inside."""
+
+    def __init__(self, unet: UNetEngine, vae, text_encoder, tokenizer, scheduler, device):
+        self.unet, self.vae, self.text_encoder, self.tokenizer, self.scheduler = unet, vae, text_encoder, tokenizer, scheduler
+        self.device = torch.device(device)
+
+
+def sd_scheduler() -> DDIMScheduler:
+    """modules/models/__init__.py:134 plus steps_offset=1 from the SD-1.x pipeline config."""
+    return DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+                         set_alpha_to_one=False, steps_offset=1)
+
+
+def load_diffusion_model(model: str = "synthetic-sd15", device: str = "cuda", preproc_args: Optional[Dict[str, Any]] = None,
+                         variant: Optional[str] = None, max_batch: int = 4, seed: int = 0,
+                         unet_state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                         vae_state_dict: Optional[Dict[str, torch.Tensor]] = None, **kwargs
+                         ) -> Tuple[EtaiPipeline, Tuple[StablePreprocess, StablePostProc]]:
+    """Same signature/return shape as the reference loader.  ``model``:
+      * "synthetic-sd15" (default; also accepted: "sd14", "CompVis/stable-diffusion-v1-4"): SD-1.x architecture with
+        seeded random-init weights, because no pretrained checkpoint exists in this environment;
+      * or pass ``unet_state_dict`` / ``vae_state_dict`` (diffusers key names) to run real weights.
+    ``variant``: "fp32" (SIMT fp32 parity path) | "fp16" | "bf16" (tcgen05 path)."""
+    variant = variant or "fp32"
+    dtype = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[variant]
+    if model not in ("synthetic-sd15", "sd14", "CompVis/stable-diffusion-v1-4"):
+        raise Exception(model)
+    if not str(device).startswith("cuda"):
+        raise RuntimeError("etai: the engine runs on CUDA devices only (no CPU fallback)")
+    dev = torch.device(device if ":" in str(device) else f"cuda:{torch.cuda.current_device()}")
+    print(f"Loading model {model} ({variant}) ...")
+    if variant == "fp32":
+        # parity mode: the torch-side VAE / text encoder must not silently drop to TF32
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    usd = unet_state_dict if unet_state_dict is not None else synthetic.random_state_dict(synthetic.unet_param_spec(), seed)
+    unet = UNetEngine(usd, dtype=dtype, device=dev, max_batch=max_batch)
+    del usd
+    vae = AutoencoderKL().eval().requires_grad_(False)
+    vae.load_state_dict(vae_state_dict if vae_state_dict is not None
+                        else synthetic.random_state_dict(synthetic.vae_param_spec(), seed + 1), strict=True)
+    vae = vae.to(dev, dtype)
+    text_encoder = make_text_encoder(seed).to(dev)
+    pipe = EtaiPipeline(unet, vae, text_encoder, SyntheticTokenizer(), sd_scheduler(), dev)
+    return pipe, (StablePreprocess(str(dev), size=512, **(preproc_args or {})), StablePostProc())

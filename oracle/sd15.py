@@ -631,6 +631,8 @@ class SyntheticTokenizer:
         return " ".join(out)
 
     def __call__(self, texts, padding="max_length", max_length=77, truncation=True, return_tensors="pt"):
+        if isinstance(texts, str):  # pnp.py:14-20 passes a bare string
+            texts = [texts]
         rows = []
         for t in texts:
             ids = self.encode(t)[:max_length]
