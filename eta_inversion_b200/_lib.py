@@ -59,6 +59,8 @@ SYMBOLS = {
     "etai_unet_set_context": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "etai_unet_forward": (C.c_int, [_vp, _vp, _f, _i32, _i32, C.POINTER(EtaiAttnCtrl), _vp, _vp]),
     "etai_unet_device_bytes": (_i64, [_vp]),
+    "etai_unet_launch_count": (_i64, [_vp]),
+    "etai_unet_profile": (C.c_int, [_vp, _i32, C.POINTER(C.c_float), C.POINTER(_i32)]),
     "etai_cfg_ddim_step": (C.c_int, [_vp, _i32, _i32, _f, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
     "etai_eta_noise_losses": (C.c_int, [_vp, _i32, _i32, _f, _vp, _vp, _f, _f, _f, _f, _vp, _i32, _i64, _vp, _vp, _vp]),
     "etai_groupnorm": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _f, _i32, _i32, _vp, _i64, _vp]),

@@ -1,6 +1,325 @@
-// tcgen05 flash self-attention (placeholder until the kernel lands: reports "unsupported" so callers use attn_simt.cu)
+// tcgen05 flash self-attention for sm_100a (f16 / bf16 operands, fp32 softmax and accumulation).
+//
+//   out[r] = softmax(Q[qrow[r]] K[krow[r]]^T * scale) V[vrow[r]]          per (row r, head h)
+//
+// CTA = 128 query rows of one (row, head); K/V are streamed in tiles of 128 keys.
+//   warp 0      : TMA producer.  Q, K, V tiles are fetched straight out of the fused [B,N,3C] qkv buffer through 4-D
+//                 tensor maps {d, heads, N, B}; the box is 64 wide along d, so for d = 40 / 80 / 160 the tail of the last
+//                 64-column atom is out of bounds and TMA zero-fills it (no padded copies of q/k/v exist).
+//   warp 1      : single-thread MMA issuer.   S_j = Q K_j^T   (UMMA 128 x 128 x 16, both operands K-major)
+//                                             O_j = P_j V_j   (UMMA 128 x d_pad x 16, A = P from smem (K-major),
+//                                                              B = V tile as it landed: MN-major, 128B swizzle)
+//   warps 2..5  : one thread per query row.  Reads its S row from TMEM (tcgen05.ld), online softmax in registers,
+//                 writes P (16-bit) into shared memory in the swizzled K-major layout, reads O_j back from TMEM and
+//                 folds it into the fp32 running output with the deferred rescale factor.
+// S is double buffered in TMEM (2 x 128 columns) so QK^T of tile j+1 overlaps the softmax of tile j; O_j uses
+// d_pad columns at column 256.  The (q,k,v) row remap carries PtP self-replacement / MasaCtrl / PnP (see etai.h).
+#include <cstring>
+#include <type_traits>
 #include "ops.cuh"
+#include "tc_common.cuh"
+
 namespace etai {
-bool attention_tc_supported(const SelfAttnArgs&) { return false; }
-void attention_tc(const SelfAttnArgs&, cudaStream_t) { throw Error(ETAI_ERR_UNSUPPORTED, "attention_tc not built"); }
+
+namespace {
+
+using namespace tc;
+
+constexpr int BQ = 128, BKV = 128, AT_THREADS = 192, ATOM_BYTES = 128 * 128;  // one [128 rows x 128 B] swizzle-atom tile
+
+struct AtParams {
+    void* out;
+    int Nq, Nk, heads, d;
+    long ldo;
+    float scale_log2e;
+    RowMap map;
+    int fmt;
+};
+
+// MN-major (N contiguous) B-operand tile, 128-byte swizzle: rows = K index at 128 B pitch, 8-row groups SBO = 1024 B,
+// 64-element N atoms LBO bytes apart.
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_f16_bmn(int fmt, int M, int N) {
+    return make_idesc_f16(fmt, M, N) | (1u << 16);  // B operand MN-major
+}
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename T, int ATOMS, int STAGES>
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+          const __grid_constant__ CUtensorMap tmV, AtParams p) {
+    constexpr int OP_BYTES = ATOMS * ATOM_BYTES;          // Q, or one K tile, or one V tile
+    constexpr int KV_BYTES = 2 * OP_BYTES;
+    constexpr int P_OFF = OP_BYTES + STAGES * KV_BYTES;
+    constexpr int BAR_OFF = P_OFF + 2 * ATOM_BYTES;
+    constexpr int DPAD = ATOMS == 1 ? 48 : ATOMS == 2 ? 80 : 160;  // UMMA N of the PV product (d = 40 / 80 / 160)
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+    uint64_t* kv_full = q_full + 1;
+    uint64_t* kv_empty = kv_full + STAGES;
+    uint64_t* s_full = kv_empty + STAGES;  // [2]
+    uint64_t* p_full = s_full + 2;
+    uint64_t* o_full = p_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * BQ, head = blockIdx.y, row = blockIdx.z;
+    const int ntiles = (p.Nk + BKV - 1) / BKV;
+    const int ksteps = (p.d + 15) / 16;  // 16-wide K steps of QK^T actually needed (the rest of the atom is zero)
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+        mbar_init(p_full, 128);
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_o = tmem_base + 256;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            mbar_expect_tx(q_full, OP_BYTES);
+#pragma unroll
+            for (int a = 0; a < ATOMS; ++a) tma_load_4d(smem + a * ATOM_BYTES, &tmQ, q_full, a * 64, head, q0, p.map.q[row]);
+            for (int j = 0; j < ntiles; ++j) {
+                int s = j % STAGES;
+                uint32_t ph = (j / STAGES) & 1;
+                mbar_wait(&kv_empty[s], ph ^ 1);
+                mbar_expect_tx(&kv_full[s], KV_BYTES);
+                unsigned char* kb = smem + OP_BYTES + s * KV_BYTES;
+#pragma unroll
+                for (int a = 0; a < ATOMS; ++a) {
+                    tma_load_4d(kb + a * ATOM_BYTES, &tmK, &kv_full[s], a * 64, head, j * BKV, p.map.k[row]);
+                    tma_load_4d(kb + OP_BYTES + a * ATOM_BYTES, &tmV, &kv_full[s], a * 64, head, j * BKV, p.map.v[row]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            const uint32_t idesc_s = make_idesc_f16(p.fmt, BQ, BKV);
+            const uint32_t idesc_o = make_idesc_f16_bmn(p.fmt, BQ, DPAD);
+            const uint32_t q_addr = smem_u32(smem);
+            const uint32_t p_addr = smem_u32(smem + P_OFF);
+            auto issue_s = [&](int j) {
+                int s = j % STAGES;
+                mbar_wait(&kv_full[s], (j / STAGES) & 1);
+                tc_fence_after();
+                uint32_t k_addr = smem_u32(smem + OP_BYTES + s * KV_BYTES);
+                for (int k = 0; k < ksteps; ++k) {
+                    uint32_t off = (uint32_t)(k >> 2) * ATOM_BYTES + (uint32_t)(k & 3) * 32;
+                    umma_f16(tmem_base + (uint32_t)(j & 1) * 128, make_smem_desc_sw128(q_addr + off),
+                             make_smem_desc_sw128(k_addr + off), idesc_s, k != 0);
+                }
+                umma_commit(&s_full[j & 1]);
+            };
+            auto issue_o = [&](int j) {
+                int s = j % STAGES;
+                mbar_wait(p_full, j & 1);
+                tc_fence_after();
+                uint32_t v_addr = smem_u32(smem + OP_BYTES + s * KV_BYTES + OP_BYTES);
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k) {
+                    uint32_t a_off = (uint32_t)(k >> 2) * ATOM_BYTES + (uint32_t)(k & 3) * 32;  // P: K-major, 2 atoms
+                    uint32_t b_off = (uint32_t)k * 16 * 128;                                     // V: 16 key rows
+                    umma_f16(tmem_o, make_smem_desc_sw128(p_addr + a_off),
+                             make_smem_desc_mn_sw128(v_addr + b_off, ATOM_BYTES), idesc_o, k != 0);
+                }
+                umma_commit(&kv_empty[s]);
+                umma_commit(o_full);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < ntiles; ++j) {
+                if (STAGES >= 2 && j + 1 < ntiles) issue_s(j + 1);  // overlaps the softmax of tile j
+                issue_o(j);
+                if (STAGES < 2 && j + 1 < ntiles) issue_s(j + 1);
+            }
+        }
+    } else {
+        // ===== softmax + output accumulation: thread = one query row =====
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        unsigned char* p_row = smem + P_OFF + r * 128;
+        float o_acc[DPAD];
+#pragma unroll
+        for (int i = 0; i < DPAD; ++i) o_acc[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f, alpha_pending = 1.f;
+
+        auto fold_o = [&](int j) {  // o_acc = o_acc * alpha + O_j
+            mbar_wait(o_full, j & 1);
+            tc_fence_after();
+            constexpr int N32 = DPAD / 32;
+#pragma unroll
+            for (int b = 0; b < N32; ++b) {
+                float v[32];
+                tmem_ld32(tmem_o + lane_addr + b * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o_acc[b * 32 + i] = fmaf(o_acc[b * 32 + i], alpha_pending, v[i]);
+            }
+            if constexpr (DPAD % 32 != 0) {
+                uint32_t rr[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]),
+                      "=r"(rr[7]), "=r"(rr[8]), "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]),
+                      "=r"(rr[14]), "=r"(rr[15])
+                    : "r"(tmem_o + lane_addr + N32 * 32)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    o_acc[N32 * 32 + i] = fmaf(o_acc[N32 * 32 + i], alpha_pending, __uint_as_float(rr[i]));
+            }
+        };
+
+        for (int j = 0; j < ntiles; ++j) {
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t s_addr = tmem_base + (uint32_t)(j & 1) * 128 + lane_addr;
+            // pass 1: row max of this tile
+            float mx = -INFINITY;
+            const int kbase = j * BKV;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BKV; c0 += 32) {
+                float v[32];
+                tmem_ld32(s_addr + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (kbase + c0 + i < p.Nk) mx = fmaxf(mx, v[i]);
+            }
+            const float m_new = fmaxf(m_run, mx);
+            const float alpha = exp2f((m_run - m_new) * p.scale_log2e);  // first tile: exp2(-inf) = 0
+            const float mb = m_new * p.scale_log2e;
+            if (j > 0) fold_o(j - 1);  // PV_{j-1} finished reading P and writing O: safe to overwrite P below
+            alpha_pending = alpha;
+            // pass 2: probabilities -> shared memory (K-major, 128B swizzle) + row sum
+            float sum = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BKV; c0 += 32) {
+                float v[32];
+                tmem_ld32(s_addr + c0, v);
+                uint32_t packed[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0 = (kbase + c0 + i < p.Nk) ? exp2f(fmaf(v[i], p.scale_log2e, -mb)) : 0.f;
+                    float p1 = (kbase + c0 + i + 1 < p.Nk) ? exp2f(fmaf(v[i + 1], p.scale_log2e, -mb)) : 0.f;
+                    sum += p0 + p1;
+                    if constexpr (sizeof(T) == 2 && std::is_same<T, __half>::value) {
+                        __half2 h = __floats2half2_rn(p0, p1);
+                        packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+                    } else {
+                        __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+                        packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+                    }
+                }
+                // 32 keys = 64 B = 4 chunks of 16 B inside atom (c0 / 64), chunk index ((c0 % 64) / 8 + q) ^ (r & 7)
+                unsigned char* atom = p_row + (c0 >> 6) * ATOM_BYTES;
+                int cbase = (c0 & 63) >> 3;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int chunk = (cbase + q) ^ (r & 7);
+                    *reinterpret_cast<uint4*>(atom + chunk * 16) =
+                        make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                }
+            }
+            l_run = l_run * alpha + sum;
+            m_run = m_new;
+            tc_fence_before();   // order the TMEM reads of S_j / O_{j-1} before the arrive
+            fence_async_smem();  // make the P stores visible to the tensor-core (async) proxy
+            mbar_arrive(p_full);
+        }
+        fold_o(ntiles - 1);
+        const int q = q0 + r;
+        if (q < p.Nq) {
+            const float inv = 1.f / l_run;
+            T* dst = reinterpret_cast<T*>(p.out) + ((long)row * p.Nq + q) * p.ldo + head * p.d;
+            constexpr int D = ATOMS == 1 ? 40 : ATOMS == 2 ? 80 : 160;
+#pragma unroll
+            for (int c = 0; c < D; c += 8) {
+                float o8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o8[i] = o_acc[c + i] * inv;
+                store8<T>(dst + c, o8);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <typename T, int ATOMS, int STAGES>
+void launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AtParams& p, dim3 grid, cudaStream_t s) {
+    constexpr int SMEM = ATOMS * ATOM_BYTES + STAGES * 2 * ATOMS * ATOM_BYTES + 2 * ATOM_BYTES + 256 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(attn_tc_k<T, ATOMS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
+    attn_tc_k<T, ATOMS, STAGES><<<grid, AT_THREADS, SMEM, s>>>(q, k, v, p);
+    KERNEL_CHECK();
+}
+
+CUtensorMap head_tmap(const void* base, int dtype, int d, int heads, int N, int B, long ld) {
+    uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)N, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)d * 2, (uint64_t)ld * 2, (uint64_t)ld * 2 * N};
+    uint32_t box[4] = {64, 1, 128, 1};
+    return make_tmap_16bit(base, dtype, 4, dims, str, box);
+}
+
+}  // namespace
+
+bool attention_tc_supported(const SelfAttnArgs& a) {
+    if (a.dtype != ETAI_F16 && a.dtype != ETAI_BF16) return false;
+    if (a.d != 40 && a.d != 80 && a.d != 160) return false;  // UMMA N of the PV product is compiled per head dim
+    if (a.ldq % 8 || a.ldk % 8 || a.ldv % 8 || a.ldo % 8) return false;
+    if (a.Nq < 1 || a.Nk < 1 || a.B > ETAI_MAX_ROWS) return false;
+    auto aligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return aligned(a.q) && aligned(a.k) && aligned(a.v) && aligned(a.out);
+}
+
+void attention_tc(const SelfAttnArgs& a, cudaStream_t s) {
+    ETAI_CHECK(attention_tc_supported(a), ETAI_ERR_UNSUPPORTED, "attention_tc: unsupported problem");
+    AtParams p;
+    memset(&p, 0, sizeof(p));
+    p.out = a.out; p.Nq = a.Nq; p.Nk = a.Nk; p.heads = a.heads; p.d = a.d; p.ldo = a.ldo;
+    p.scale_log2e = a.scale * 1.4426950408889634f;
+    p.map = a.map;
+    p.fmt = a.dtype == ETAI_BF16 ? 1 : 0;
+    CUtensorMap tq = head_tmap(a.q, a.dtype, a.d, a.heads, a.Nq, a.B, a.ldq);
+    CUtensorMap tk = head_tmap(a.k, a.dtype, a.d, a.heads, a.Nk, a.B, a.ldk);
+    CUtensorMap tv = head_tmap(a.v, a.dtype, a.d, a.heads, a.Nk, a.B, a.ldv);
+    dim3 grid(cdiv(a.Nq, BQ), a.heads, a.B);
+#define LAUNCH(T)                                                              \
+    do {                                                                       \
+        if (a.d == 40) launch_attn<T, 1, 2>(tq, tk, tv, p, grid, s);           \
+        else if (a.d == 80) launch_attn<T, 2, 2>(tq, tk, tv, p, grid, s);      \
+        else launch_attn<T, 3, 1>(tq, tk, tv, p, grid, s);                     \
+    } while (0)
+    if (a.dtype == ETAI_F16) LAUNCH(__half);
+    else LAUNCH(__nv_bfloat16);
+#undef LAUNCH
+}
+
 }  // namespace etai

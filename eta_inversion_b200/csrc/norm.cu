@@ -30,7 +30,7 @@ static GnPlan gn_plan(long HW, int C) {
     if (p.R < 1) p.R = 1;
     p.threads = (p.cvecs * p.R + 31) / 32 * 32;  // whole warps; the tail threads only help in the fold
     long rpc = 32;
-    while (cdiv(HW, rpc) > GN_MAX_CHUNKS) rpc *= 2;
+    while (cdiv(HW, rpc) > 32) rpc *= 2;  // <= 32 chunks: the apply kernel folds them with one lane per chunk
     if (rpc > HW) rpc = HW;
     p.rows_per_chunk = (int)rpc;
     p.chunks = cdiv(HW, rpc);
@@ -146,8 +146,11 @@ void groupnorm(const void* x, void* y, const void* gamma, const void* beta, int 
     GnPlan p = gn_plan(HW, C);
     size_t smem = (size_t)2 * p.R * C * sizeof(float);
     long vecs = HW * C / 8;
-    int ablocks = (int)((vecs + 255) / 256);
-    if (ablocks > 148 * 8) ablocks = 148 * 8;
+    // apply grid: ~4 CTAs per SM in total (each CTA re-derives mean/rstd from <= 32 chunk partials, then grid-strides)
+    int ablocks = (int)((vecs + 1023) / 1024);
+    int cap = (148 * 4 + B - 1) / B;
+    if (ablocks > cap) ablocks = cap;
+    if (ablocks < 1) ablocks = 1;
     ETAI_DISPATCH_DTYPE(dtype, T, {
         gn_stats_k<T><<<dim3(p.chunks, B), p.threads, smem, s>>>((const T*)x, (double*)ws, HW, C, groups, p.cvecs, p.R,
                                                                  p.rows_per_chunk, p.chunks);

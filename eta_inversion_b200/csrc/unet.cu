@@ -82,6 +82,27 @@ struct etai_unet {
     size_t tc_ws_bytes = 0;
     size_t workspace_bytes = 0;
 
+    // ---- instrumentation: launch counter (always) + per-category CUDA-event timing (opt-in) -----
+    int64_t launches = 0;
+    bool prof_on = false;
+    struct ProfRec { int cat; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof_recs;
+    cudaEvent_t prof_begin(cudaStream_t s) {
+        if (!prof_on || !arena.base) return nullptr;
+        cudaEvent_t e;
+        CUDA_CHECK(cudaEventCreate(&e));
+        CUDA_CHECK(cudaEventRecord(e, s));
+        return e;
+    }
+    void prof_end(int cat, cudaEvent_t a, int n_launches, cudaStream_t s) {
+        if (arena.base) launches += n_launches;
+        if (!a) return;
+        cudaEvent_t b;
+        CUDA_CHECK(cudaEventCreate(&b));
+        CUDA_CHECK(cudaEventRecord(b, s));
+        prof_recs.push_back({cat, a, b});
+    }
+
     // ---- weight loading helpers -------------------------------------------------------------
     std::unordered_map<std::string, const etai_tensor*> table;
     float* stage = nullptr;
@@ -230,8 +251,11 @@ struct etai_unet {
     // ---- op wrappers --------------------------------------------------------------------------
     void gemm(GemmArgs& a, cudaStream_t s) {
         a.dtype = dt;
-        if (tc && gemm_tc_supported(a)) gemm_tc(a, tc_ws, tc_ws_bytes, s);
+        cudaEvent_t e = prof_begin(s);
+        bool use_tc = tc && gemm_tc_supported(a);
+        if (use_tc) gemm_tc(a, tc_ws, tc_ws_bytes, s);
         else gemm_simt(a, s);
+        prof_end(a.conv ? ETAI_PROF_CONV : ETAI_PROF_GEMM, e, (use_tc && a.conv && a.stride == 2) ? 2 : 1, s);
     }
     void* linear(const void* x, long M, const Lin& l, const void* residual, cudaStream_t s, int geglu = 0) {
         int nout = geglu ? l.n / 2 : l.n;
@@ -257,12 +281,20 @@ struct etai_unet {
     }
     void* gnorm(const void* x, int B, long HW, const Norm& n, float eps, bool silu, cudaStream_t s) {
         void* y = arena.alloc((size_t)B * HW * n.c * esz);
-        if (arena.base) groupnorm(x, y, n.g, n.b, B, HW, n.c, 32, eps, silu, dt, gn_ws, s);
+        if (arena.base) {
+            cudaEvent_t e = prof_begin(s);
+            groupnorm(x, y, n.g, n.b, B, HW, n.c, 32, eps, silu, dt, gn_ws, s);
+            prof_end(ETAI_PROF_GROUPNORM, e, 2, s);
+        }
         return y;
     }
     void* lnorm(const void* x, long M, const Norm& n, cudaStream_t s) {
         void* y = arena.alloc((size_t)M * n.c * esz);
-        if (arena.base) layernorm(x, y, n.g, n.b, M, n.c, 1e-5f, dt, s);
+        if (arena.base) {
+            cudaEvent_t e = prof_begin(s);
+            layernorm(x, y, n.g, n.b, M, n.c, 1e-5f, dt, s);
+            prof_end(ETAI_PROF_LAYERNORM, e, 1, s);
+        }
         return y;
     }
     void* resnet(const void* x, int B, int H, int W, const Res& r, const etai_attn_ctrl* ctrl, bool inject_here,
@@ -279,8 +311,10 @@ struct etai_unet {
             ETAI_CHECK(B == 3 * inj, ETAI_ERR_ARG, "pnp injection expects B == 3*inject_rows");
             void* o = conv3x3(a2, B, H, W, r.c2, 1, nullptr, nullptr, s);
             if (arena.base) {
+                cudaEvent_t e = prof_begin(s);
                 copy_rows(o, HW * r.cout, 0, inj, inj, 2 * inj, dt, s);
                 add_inplace(o, skip, M * r.cout, dt, s);
+                prof_end(ETAI_PROF_OTHER, e, 2, s);
             }
             return o;
         }
@@ -380,8 +414,10 @@ void* etai_unet::transformer(const void* x, int B, int H, int W, const Tfm& t, c
             ETAI_CHECK(a.map.q[r] >= 0 && a.map.q[r] < B && a.map.k[r] >= 0 && a.map.k[r] < B && a.map.v[r] >= 0 &&
                            a.map.v[r] < B, ETAI_ERR_ARG, "self remap row out of range");
         }
+        cudaEvent_t e = prof_begin(s);
         if (tc && attention_tc_supported(a)) attention_tc(a, s);
         else attention_simt(a, s);
+        prof_end(ETAI_PROF_SELF_ATTN, e, 1, s);
     }
     h = linear(ao, M, t.o1, h, s);
     // ---- cross attention ----
@@ -422,7 +458,9 @@ void* etai_unet::transformer(const void* x, int B, int H, int W, const Tfm& t, c
         for (int r = 0; r < B; ++r)
             if (!used[r]) a.groups[ng++] = CrossGroup{r, -1, 0, slot_of[r], -1};
         a.n_groups = ng;
+        cudaEvent_t e = prof_begin(s);
         cross_attention(a, s);
+        prof_end(ETAI_PROF_CROSS_ATTN, e, 1, s);
     }
     h = linear(co, M, t.o2, h, s);
     // ---- feed forward (GEGLU) ----
@@ -436,6 +474,7 @@ void etai_unet::set_context(const void* ctx, int io_dtype, int B, cudaStream_t s
     ETAI_CHECK(B >= 1 && B <= cfg.max_batch, ETAI_ERR_ARG, "set_context: batch out of range");
     long M = (long)B * cfg.ctx_len;
     convert(ctx, io_dtype, ctx_buf, dt, M * cfg.cross_dim, s);
+    launches += 1;
     GemmArgs a;
     a.A = ctx_buf; a.W = kv_all.w; a.C = kv_cache;
     a.M = M; a.N = kv_all.n; a.K = kv_all.k; a.lda = kv_all.k; a.ldc = kv_all.n;
@@ -457,14 +496,20 @@ void etai_unet::forward(const void* latent, float t, int io_dtype, int B, const 
 
     // time embedding (t is shared by all rows): all fp32, M = 1 skinny GEMMs
     if (!planning) {
+        cudaEvent_t e = prof_begin(s);
         timestep_sincos(t, tbuf + TB_SIN, c[0], s);
         skinny_linear(tbuf + TB_SIN, time1.w, time1.b, tbuf + TB_H1, 1, temb, c[0], 1, dt, s);        // silu(linear_1)
         skinny_linear(tbuf + TB_H1, time2.w, time2.b, tbuf + TB_ST, 1, temb, temb, 1, dt, s);          // silu(temb)
         skinny_linear(tbuf + TB_ST, temb_all.w, temb_all.b, tbuf + TB_PROJ, 1, temb_all.n, temb, 0, dt, s);
+        prof_end(ETAI_PROF_OTHER, e, 4, s);
     }
 
     void* x = arena.alloc((size_t)B * H * W * 4 * esz);
-    if (!planning) nchw_to_nhwc(latent, io_dtype, x, dt, B, 4, (long)H * W, s);
+    if (!planning) {
+        cudaEvent_t e = prof_begin(s);
+        nchw_to_nhwc(latent, io_dtype, x, dt, B, 4, (long)H * W, s);
+        prof_end(ETAI_PROF_OTHER, e, 1, s);
+    }
     void* h = conv3x3(x, B, H, W, conv_in, 1, nullptr, nullptr, s);
 
     struct Skip { void* p; int C; };
@@ -492,7 +537,11 @@ void etai_unet::forward(const void* latent, float t, int io_dtype, int B, const 
             skips.pop_back();
             long rows = (long)B * H * W;
             void* cat = arena.alloc((size_t)rows * (hc + sk.C) * esz);
-            if (!planning) concat_channels(h, hc, sk.p, sk.C, cat, rows, dt, s);
+            if (!planning) {
+                cudaEvent_t e = prof_begin(s);
+                concat_channels(h, hc, sk.p, sk.C, cat, rows, dt, s);
+                prof_end(ETAI_PROF_OTHER, e, 1, s);
+            }
             const Res& r = up_res[i][j];
             ETAI_CHECK(r.cin == hc + sk.C, ETAI_ERR_STATE, "skip bookkeeping mismatch");
             h = resnet(cat, B, H, W, r, ctrl, i == 1 && j == 1, s);
@@ -501,14 +550,22 @@ void etai_unet::forward(const void* latent, float t, int io_dtype, int B, const 
         }
         if (i < 3) {
             void* up = arena.alloc((size_t)B * H * W * 4 * hc * esz);
-            if (!planning) upsample2x(h, up, B, H, W, hc, dt, s);
+            if (!planning) {
+                cudaEvent_t e = prof_begin(s);
+                upsample2x(h, up, B, H, W, hc, dt, s);
+                prof_end(ETAI_PROF_OTHER, e, 1, s);
+            }
             H *= 2; W *= 2;
             h = conv3x3(up, B, H, W, up_samp[i], 1, nullptr, nullptr, s);
         }
     }
     void* a = gnorm(h, B, (long)H * W, norm_out, 1e-5f, true, s);
     void* o = conv3x3(a, B, H, W, conv_out, 1, nullptr, nullptr, s);
-    if (!planning) nhwc_to_nchw(o, dt, eps_out, io_dtype, B, 4, (long)H * W, s);
+    if (!planning) {
+        cudaEvent_t e = prof_begin(s);
+        nhwc_to_nchw(o, dt, eps_out, io_dtype, B, 4, (long)H * W, s);
+        prof_end(ETAI_PROF_OTHER, e, 1, s);
+    }
 }
 
 void etai_unet::plan_workspace() {
@@ -618,6 +675,30 @@ int etai_unet_destroy(etai_unet* h) {
     if (h->stage) cudaFree(h->stage);
     delete h;
     return ETAI_OK;
+}
+
+int64_t etai_unet_launch_count(const etai_unet* h) { return h ? h->launches : 0; }
+
+int etai_unet_profile(etai_unet* h, int32_t enable, float* ms_out, int32_t* launches_out) {
+    ETAI_API_BEGIN
+    ETAI_CHECK(h, ETAI_ERR_ARG, "profile: null handle");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    float ms[ETAI_PROF_NCAT] = {0};
+    int32_t cnt[ETAI_PROF_NCAT] = {0};
+    for (auto& r : h->prof_recs) {
+        CUDA_CHECK(cudaEventSynchronize(r.b));
+        float t = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.cat] += t;
+        cnt[r.cat] += 1;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    h->prof_recs.clear();
+    if (ms_out) for (int i = 0; i < ETAI_PROF_NCAT; ++i) ms_out[i] = ms[i];
+    if (launches_out) for (int i = 0; i < ETAI_PROF_NCAT; ++i) launches_out[i] = cnt[i];
+    h->prof_on = enable != 0;
+    ETAI_API_END
 }
 
 int64_t etai_unet_device_bytes(const etai_unet* h) { return h ? (int64_t)(h->weight_bytes + h->workspace_bytes) : 0; }

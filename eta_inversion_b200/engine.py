@@ -18,6 +18,7 @@ from ._lib import (CTRL_CROSS_EDIT, CTRL_CROSS_STORE, CTRL_SELF_REMAP, MATH_AUTO
                    EtaiUnetCfg, check, dtype_code, i32_array, ptr, stream_ptr)
 
 SD15_CHANNELS = (320, 640, 1280, 1280)
+LAUNCHES = [0]  # kernels launched through the op-level entry points below (the UNet handle counts its own)
 
 
 def _require_cuda(t: torch.Tensor, name: str) -> None:
@@ -159,6 +160,18 @@ class UNetEngine:
     def device_bytes(self) -> int:
         return int(self._lib.etai_unet_device_bytes(self._h))
 
+    PROF_CATEGORIES = ("conv3x3", "gemm", "self_attn", "cross_attn", "groupnorm", "layernorm", "other")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.etai_unet_launch_count(self._h))
+
+    def profile(self, enable: bool) -> Dict[str, Dict[str, float]]:
+        """Read+clear the per-category device time recorded since the last call, then switch recording on/off."""
+        ms, cnt = (C.c_float * 7)(), (C.c_int32 * 7)()
+        check(self._lib.etai_unet_profile(self._h, int(enable), ms, cnt))
+        return {n: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, n in enumerate(self.PROF_CATEGORIES)}
+
     def set_context(self, ctx: torch.Tensor) -> None:
         _require_cuda(ctx, "encoder_hidden_states")
         if ctx.ndim != 3 or ctx.shape[1] != self.ctx_len or ctx.shape[2] != self.cross_dim:
@@ -274,6 +287,7 @@ def cfg_ddim_step(eps, x, a_from: float, a_to: float, guidance: Optional[float] 
     check(_lib.load().etai_cfg_ddim_step(ptr(eps), n, int(has_cfg), float(guidance or 0.0), ptr(x), ptr(out), ptr(eps_out),
                                          float(a_from), float(a_to), float(eta), float(variance), ptr(eta_map),
                                          ptr(noise_cand), ptr(losses), K, ptr(pin_src), E, stream_ptr()))
+    LAUNCHES[0] += 1
     return (out, eps_out) if want_eps else out
 
 
@@ -287,4 +301,5 @@ def eta_noise_losses(eps, x, x_prev_inv, a_from: float, a_to: float, guidance: O
     check(_lib.load().etai_eta_noise_losses(ptr(eps), n, int(guidance is not None), float(guidance or 0.0), ptr(x),
                                             ptr(x_prev_inv), float(a_from), float(a_to), float(eta), float(variance),
                                             ptr(noise_cand), K, E, ptr(losses), ptr(best), stream_ptr()))
+    LAUNCHES[0] += 2
     return losses, best

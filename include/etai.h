@@ -146,6 +146,15 @@ ETAI_EXPORT int etai_unet_set_context(etai_unet* h, const void* ctx, int32_t io_
 ETAI_EXPORT int etai_unet_forward(etai_unet* h, const void* latent, float t, int32_t io_dtype, int32_t B,
                       const etai_attn_ctrl* ctrl, void* eps_out, void* stream);
 
+/* Instrumentation.  etai_unet_launch_count: kernels launched by this handle since create (the bench's
+ * `gpu_launches` claim).  etai_unet_profile: reads (and clears) the per-category device time accumulated since the
+ * previous call -- CUDA events recorded around every op on the caller's stream -- then switches recording on/off.
+ * ms_out / launches_out: [ETAI_PROF_NCAT] or NULL.  Recording adds event overhead; never time a bench with it on. */
+enum { ETAI_PROF_CONV = 0, ETAI_PROF_GEMM = 1, ETAI_PROF_SELF_ATTN = 2, ETAI_PROF_CROSS_ATTN = 3,
+       ETAI_PROF_GROUPNORM = 4, ETAI_PROF_LAYERNORM = 5, ETAI_PROF_OTHER = 6, ETAI_PROF_NCAT = 7 };
+ETAI_EXPORT int64_t etai_unet_launch_count(const etai_unet* h);
+ETAI_EXPORT int etai_unet_profile(etai_unet* h, int32_t enable, float* ms_out, int32_t* launches_out);
+
 /* Bytes of device memory held by the handle (weights + workspace). */
 ETAI_EXPORT int64_t etai_unet_device_bytes(const etai_unet* h);
 

@@ -146,6 +146,27 @@ def test_attention_simt_fp32(N, d):
     assert _relerr(out, ref.float()) < 2e-5
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,d", [(4096, 40), (1024, 80), (256, 160), (64, 160), (200, 40), (1024, 40)])
+def test_attention_tc(dtype, N, d):
+    """tcgen05 flash attention (TMA zero-padded head dims, MN-major V operand) vs fp32 SDPA on the same inputs."""
+    from eta_inversion_b200 import engine as E
+    B, heads = 3, 8
+    C = heads * d
+    qkv = _rand((B, N, 3 * C), 1).to(dtype).cuda()
+    q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    rows = ([0, 0, 2], [0, 0, 1], [0, 1, 2])
+    out = E.attention(q, k, v, heads, rows=rows)
+
+    def sh(t):
+        return t.float().reshape(B, N, heads, d).permute(0, 2, 1, 3)
+    qq, kk, vv = sh(q)[list(rows[0])], sh(k)[list(rows[1])], sh(v)[list(rows[2])]
+    ref = F.scaled_dot_product_attention(qq, kk, vv).permute(0, 2, 1, 3).reshape(B, N, C)
+    err = _relerr(out.float(), ref)
+    print(f"attention_tc {dtype} N={N} d={d}: rel err {err:.2e}")
+    assert err < (4e-3 if dtype == torch.float16 else 2e-2)
+
+
 def test_scheduler_step_matches_closed_form():
     from eta_inversion_b200 import engine as E
     n, Esz = 2, 4 * 64 * 64
