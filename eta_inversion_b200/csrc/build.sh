@@ -4,7 +4,7 @@ set -euo pipefail
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr -DETAI_BUILD"
-SRCS="elementwise norm gemm_simt attn_simt cross_attn gemm_tc attn_tc unet api"
+SRCS="elementwise norm gemm_simt attn_simt cross_attn gemm_tc attn_tc cross_attn_tc unet api"
 mkdir -p build
 pids=()
 for s in $SRCS; do

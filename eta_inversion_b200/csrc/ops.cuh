@@ -76,7 +76,9 @@ struct CrossAttnArgs {
     float* store;  // [slots][N][L] fp32 accumulators or null
     int dtype;
 };
-void cross_attention(const CrossAttnArgs& a, cudaStream_t s);
+void cross_attention(const CrossAttnArgs& a, cudaStream_t s);       // SIMT, fp32 math (parity path)
+void cross_attention_tc(const CrossAttnArgs& a, cudaStream_t s);    // tcgen05 (16-bit engine)
+bool cross_attention_tc_supported(const CrossAttnArgs& a);
 
 // ---------------- data movement / elementwise -------------------------------------------------
 void nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int B, int C, long HW, cudaStream_t s);

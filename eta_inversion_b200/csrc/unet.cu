@@ -459,7 +459,8 @@ void* etai_unet::transformer(const void* x, int B, int H, int W, const Tfm& t, c
             if (!used[r]) a.groups[ng++] = CrossGroup{r, -1, 0, slot_of[r], -1};
         a.n_groups = ng;
         cudaEvent_t e = prof_begin(s);
-        cross_attention(a, s);
+        if (tc && cross_attention_tc_supported(a)) cross_attention_tc(a, s);
+        else cross_attention(a, s);
         prof_end(ETAI_PROF_CROSS_ATTN, e, 1, s);
     }
     h = linear(co, M, t.o2, h, s);

@@ -165,8 +165,9 @@ class AttentionControlEdit(AttentionStore):
         self.prompts = prompts
         self.attn_replace_thres = attn_replace_thres or 32 ** 2
         self.batch_size = len(prompts)
-        self.cross_replace_alpha = ptp_utils.get_time_words_attention_alpha(
-            prompts, num_steps, cross_replace_steps, model.tokenizer).to(model.device)
+        alpha_host = ptp_utils.get_time_words_attention_alpha(prompts, num_steps, cross_replace_steps, model.tokenizer)
+        self._alpha_active = [bool(a.any()) for a in alpha_host]  # host copy: skip the edit when a step's alpha is all 0
+        self.cross_replace_alpha = alpha_host.to(model.device)
         if type(self_replace_steps) is float:
             self_replace_steps = 0, self_replace_steps
         self.num_self_replace = int(num_steps * self_replace_steps[0]), int(num_steps * self_replace_steps[1])
@@ -191,9 +192,10 @@ class AttentionControlEdit(AttentionStore):
         ctrl = super().begin_forward(unet, batch_rows)
         src, tgt = batch_rows // 2, batch_rows // 2 + 1  # rows [u_src, u_tgt, c_src, c_tgt]
         mapper, blend_a, eq = self.edit_tables()
-        ctrl.edit_pairs = [(src, tgt)]
-        ctrl.mapper, ctrl.blend_a, ctrl.equalizer = mapper.contiguous(), blend_a.contiguous(), eq.contiguous()
-        ctrl.alpha_step = self.cross_replace_alpha[self.cur_step].reshape(1, MAX_NUM_WORDS).float().contiguous()
+        if self._alpha_active[self.cur_step]:  # alpha == 0 for every word leaves P_tgt untouched (ptp.py:209-210)
+            ctrl.edit_pairs = [(src, tgt)]
+            ctrl.mapper, ctrl.blend_a, ctrl.equalizer = mapper.contiguous(), blend_a.contiguous(), eq.contiguous()
+            ctrl.alpha_step = self.cross_replace_alpha[self.cur_step].reshape(1, MAX_NUM_WORDS).float().contiguous()
         if self.num_self_replace[0] <= self.cur_step < self.num_self_replace[1]:
             rows = list(range(batch_rows))
             qk = list(rows)
