@@ -6,23 +6,24 @@ namespace etai {
 // ---------------------------------------------------------------------------------------------
 // layout conversion at the ABI boundary (latents are NCHW [B,4,64,64] in the reference)
 // ---------------------------------------------------------------------------------------------
+// Cp >= C: output channels [C, Cp) are zero (pads the 4-channel latent to one 64-wide K block for the tcgen05 conv)
 template <typename TI, typename TO>
-__global__ void nchw_to_nhwc_k(const TI* __restrict__ in, TO* __restrict__ out, int C, long HW, long total) {
+__global__ void nchw_to_nhwc_k(const TI* __restrict__ in, TO* __restrict__ out, int C, int Cp, long HW, long total) {
     long i = blockIdx.x * (long)blockDim.x + threadIdx.x;  // index into NHWC output
     if (i >= total) return;
-    int c = (int)(i % C);
-    long p = (i / C) % HW;
-    long b = i / (C * HW);
-    out[i] = from_f<TO>(to_f<TI>(in[(b * C + c) * HW + p]));
+    int c = (int)(i % Cp);
+    long p = (i / Cp) % HW;
+    long b = i / (Cp * HW);
+    out[i] = c < C ? from_f<TO>(to_f<TI>(in[(b * C + c) * HW + p])) : from_f<TO>(0.f);
 }
 template <typename TI, typename TO>
-__global__ void nhwc_to_nchw_k(const TI* __restrict__ in, TO* __restrict__ out, int C, long HW, long total) {
-    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;  // index into NCHW output
+__global__ void nhwc_to_nchw_k(const TI* __restrict__ in, TO* __restrict__ out, int C, int Cp, long HW, long total) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;  // index into NCHW output; input rows are Cp wide
     if (i >= total) return;
     long p = i % HW;
     int c = (int)((i / HW) % C);
     long b = i / (C * HW);
-    out[i] = from_f<TO>(to_f<TI>(in[(b * HW + p) * C + c]));
+    out[i] = from_f<TO>(to_f<TI>(in[(b * HW + p) * Cp + c]));
 }
 template <typename TI, typename TO>
 __global__ void convert_k(const TI* __restrict__ in, TO* __restrict__ out, long n) {
@@ -33,16 +34,16 @@ __global__ void convert_k(const TI* __restrict__ in, TO* __restrict__ out, long 
 #define DISPATCH2(dti, dto, TI, TO, ...) \
     ETAI_DISPATCH_DTYPE(dti, TI, ETAI_DISPATCH_DTYPE(dto, TO, __VA_ARGS__))
 
-void nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int B, int C, long HW, cudaStream_t s) {
-    long total = (long)B * C * HW;
+void nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int B, int C, int Cp, long HW, cudaStream_t s) {
+    long total = (long)B * Cp * HW;
     DISPATCH2(in_dtype, out_dtype, TI, TO,
-              (nchw_to_nhwc_k<TI, TO><<<cdiv(total, 256), 256, 0, s>>>((const TI*)in, (TO*)out, C, HW, total)));
+              (nchw_to_nhwc_k<TI, TO><<<cdiv(total, 256), 256, 0, s>>>((const TI*)in, (TO*)out, C, Cp, HW, total)));
     KERNEL_CHECK();
 }
-void nhwc_to_nchw(const void* in, int in_dtype, void* out, int out_dtype, int B, int C, long HW, cudaStream_t s) {
+void nhwc_to_nchw(const void* in, int in_dtype, void* out, int out_dtype, int B, int C, int Cp, long HW, cudaStream_t s) {
     long total = (long)B * C * HW;
     DISPATCH2(in_dtype, out_dtype, TI, TO,
-              (nhwc_to_nchw_k<TI, TO><<<cdiv(total, 256), 256, 0, s>>>((const TI*)in, (TO*)out, C, HW, total)));
+              (nhwc_to_nchw_k<TI, TO><<<cdiv(total, 256), 256, 0, s>>>((const TI*)in, (TO*)out, C, Cp, HW, total)));
     KERNEL_CHECK();
 }
 void convert(const void* in, int in_dtype, void* out, int out_dtype, long n, cudaStream_t s) {
@@ -218,17 +219,17 @@ void skinny_linear(const float* x, const void* W, const void* bias, float* out, 
 // weight repack (runs once at create): OIHW fp32 -> [O][ky][kx][I] T ; GEGLU row interleave
 // ---------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void pack_conv_k(const float* __restrict__ w, T* __restrict__ out, int O, int I, long total) {
-    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;  // index into output [O][9][I]
+__global__ void pack_conv_k(const float* __restrict__ w, T* __restrict__ out, int O, int I, int Ip, long total) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;  // index into output [Op][9][Ip] (zero padded)
     if (i >= total) return;
-    int c = (int)(i % I);
-    int tap = (int)((i / I) % 9);
-    long o = i / (9L * I);
-    out[i] = from_f<T>(w[(o * I + c) * 9 + tap]);
+    int c = (int)(i % Ip);
+    int tap = (int)((i / Ip) % 9);
+    long o = i / (9L * Ip);
+    out[i] = (o < O && c < I) ? from_f<T>(w[(o * I + c) * 9 + tap]) : from_f<T>(0.f);
 }
-void pack_conv_weight(const float* oihw, void* out, int O, int I, int dtype, cudaStream_t s) {
-    long total = 9L * O * I;
-    ETAI_DISPATCH_DTYPE(dtype, T, (pack_conv_k<T><<<cdiv(total, 256), 256, 0, s>>>(oihw, (T*)out, O, I, total)));
+void pack_conv_weight(const float* oihw, void* out, int O, int I, int Op, int Ip, int dtype, cudaStream_t s) {
+    long total = 9L * Op * Ip;
+    ETAI_DISPATCH_DTYPE(dtype, T, (pack_conv_k<T><<<cdiv(total, 256), 256, 0, s>>>(oihw, (T*)out, O, I, Ip, total)));
     KERNEL_CHECK();
 }
 // ff.net.0.proj: rows [0,N2/2) are the value half, [N2/2,N2) the gate half (chunk(2,-1)). Interleave so that the

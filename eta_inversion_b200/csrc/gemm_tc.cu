@@ -54,22 +54,25 @@ namespace {
 
 using namespace tc;
 
-constexpr int BM = 128, BK = 64, UMMA_K = 16, GT_THREADS = 192;
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int EPI_WARPS = 8, GT_THREADS = 32 * (2 + EPI_WARPS);  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 
 struct TcParams {
     void* C;
     const void* bias;      // [N] storage dtype or null
     const float* bias2;    // [N] fp32 or null (time-embedding projection)
     const void* residual;  // [M,ldr] or null
+    float* partial;        // split-K: fp32 [splits][M][N] workspace (epilogue deferred to splitk_reduce_k)
     long M;
     int N;
     long ldc, ldr;
     int geglu;
-    int num_kb;            // K blocks of 64
+    int num_kb;            // K blocks of 64 (whole problem)
+    int splits, kb_per_split;
+    int tiles_m, tiles_n;
     // conv geometry
     int cin_blocks;        // Cin / 64
     int Himg, Wimg;        // output == input spatial size (stride 1)
-    int bw, bh, bb;        // box in pixels
     int fmt;               // 0 f16, 1 bf16
 };
 
@@ -81,29 +84,34 @@ struct Smem {
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + slack for manual 1024-B alignment
-    static constexpr int TMEM_COLS = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;  // TMEM columns between the two accumulator buffers
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
 };
 
+// Persistent kernel: grid = min(#work items, #SMs); every role walks the same static schedule
+//   item = blockIdx.x + i * gridDim.x ;  (split, m_tile, n_tile) = decode(item)
+// The smem ring runs across items, the accumulator is double buffered in TMEM so the epilogue of item i overlaps
+// the main loop of item i+1.
 template <typename T, int BN, bool CONV>
 __global__ void __launch_bounds__(GT_THREADS, 1)
-gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams p) {
     using S = Smem<BN>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint64_t* empty = full + S::STAGES;
-    uint64_t* accum_full = empty + S::STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+    uint64_t* acc_full = empty + S::STAGES;   // [2]
+    uint64_t* acc_empty = acc_full + 2;       // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN;
-    const long m0 = (long)blockIdx.y * BM;
+    const int items = p.tiles_m * p.tiles_n * p.splits;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(accum_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
@@ -115,117 +123,200 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            int b0 = 0, oy0 = 0;
-            if (CONV) {
-                long hw = (long)p.Himg * p.Wimg;
-                b0 = (int)(m0 / hw);
-                oy0 = (int)((m0 % hw) / p.Wimg);
-            }
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                int s = kb % S::STAGES;
-                uint32_t ph = (kb / S::STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], S::STAGE_BYTES);
-                unsigned char* sa = smem + s * S::STAGE_BYTES;
-                unsigned char* sb = sa + S::A_BYTES;
+            int kc = 0;  // k blocks issued so far by this CTA (ring position)
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int tile = item % (p.tiles_m * p.tiles_n), split = item / (p.tiles_m * p.tiles_n);
+                const int n0 = (tile % p.tiles_n) * BN;
+                const long m0 = (long)(tile / p.tiles_n) * BM;
+                int b0 = 0, oy0 = 0;
                 if (CONV) {
-                    int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
-                    tma_load_4d(sa, &tmA, &full[s], cb * BK, tap % 3 - 1, oy0 + tap / 3 - 1, b0);
-                } else {
-                    tma_load_2d(sa, &tmA, &full[s], kb * BK, (int)m0);
+                    long hw = (long)p.Himg * p.Wimg;
+                    b0 = (int)(m0 / hw);
+                    oy0 = (int)((m0 % hw) / p.Wimg);
                 }
-                tma_load_2d(sb, &tmB, &full[s], kb * BK, n0);
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = kb0 + p.kb_per_split < p.num_kb ? kb0 + p.kb_per_split : p.num_kb;
+                for (int kb = kb0; kb < kb1; ++kb, ++kc) {
+                    int s = kc % S::STAGES;
+                    uint32_t ph = (kc / S::STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], S::STAGE_BYTES);
+                    unsigned char* sa = smem + s * S::STAGE_BYTES;
+                    unsigned char* sb = sa + S::A_BYTES;
+                    if (CONV) {
+                        int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
+                        tma_load_4d(sa, &tmA, &full[s], cb * BK, tap % 3 - 1, oy0 + tap / 3 - 1, b0);
+                    } else {
+                        tma_load_2d(sa, &tmA, &full[s], kb * BK, (int)m0);
+                    }
+                    tma_load_2d(sb, &tmB, &full[s], kb * BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
             const uint32_t idesc = make_idesc_f16(p.fmt, BM, BN);
-            for (int kb = 0; kb < p.num_kb; ++kb) {
-                int s = kb % S::STAGES;
-                uint32_t ph = (kb / S::STAGES) & 1;
-                mbar_wait(&full[s], ph);
+            int kc = 0, li = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
+                const int split = item / (p.tiles_m * p.tiles_n);
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = kb0 + p.kb_per_split < p.num_kb ? kb0 + p.kb_per_split : p.num_kb;
+                const int buf = li & 1;
+                mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
-                uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES);
-                uint64_t da = make_smem_desc_sw128(sa);
-                uint64_t db = make_smem_desc_sw128(sa + S::A_BYTES);
+                const uint32_t tacc = tmem_base + (uint32_t)buf * S::ACC_STRIDE;
+                for (int kb = kb0; kb < kb1; ++kb, ++kc) {
+                    int s = kc % S::STAGES;
+                    uint32_t ph = (kc / S::STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES);
+                    uint64_t da = make_smem_desc_sw128(sa);
+                    uint64_t db = make_smem_desc_sw128(sa + S::A_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    // advance 16 elements (32 B) along K inside the 128-B swizzle atom: +2 in the (addr>>4) field
-                    umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advance 16 elements (32 B) along K inside the 128-B swizzle atom: +2 in the (addr>>4) field
+                        umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0) || (k > 0));
+                    }
+                    umma_commit(&empty[s]);  // frees the smem stage once these MMAs retire
                 }
-                umma_commit(&empty[s]);  // frees the smem stage once these MMAs retire
+                umma_commit(&acc_full[buf]);
             }
-            umma_commit(accum_full);
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-        mbar_wait(accum_full, 0);
-        tc_fence_after();
+        // ===== epilogue: warps 2..9.  TMEM lane quarter = warp % 4; the two warps of a quarter alternate 32-col chunks
         const int quarter = warp & 3;
-        const long m = m0 + quarter * 32 + lane;
-        const bool row_ok = m < p.M;
+        const int half = (warp - 2) >> 2;
         T* C = reinterpret_cast<T*>(p.C);
         const T* bias = reinterpret_cast<const T*>(p.bias);
         const T* res = reinterpret_cast<const T*>(p.residual);
+        int li = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
+            const int tile = item % (p.tiles_m * p.tiles_n), split = item / (p.tiles_m * p.tiles_n);
+            const int n0 = (tile % p.tiles_n) * BN;
+            const long m0 = (long)(tile / p.tiles_n) * BM;
+            const int buf = li & 1;
+            mbar_wait(&acc_full[buf], (li >> 1) & 1);
+            tc_fence_after();
+            const long m = m0 + quarter * 32 + lane;
+            const bool row_ok = m < p.M;
+            const uint32_t tacc = tmem_base + (uint32_t)buf * S::ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);  // warp-collective
-            const int n = n0 + c0;
-            if (!row_ok || n >= p.N) continue;
-            if (bias) {
+            for (int c0 = half * 32; c0 < BN; c0 += 64) {
+                float v[32];
+                tmem_ld32(tacc + (uint32_t)c0, v);  // warp-collective
+                const int n = n0 + c0;
+                if (!row_ok || n >= p.N) continue;
+                if (p.partial) {  // split-K: raw fp32 partial sums, epilogue happens in splitk_reduce_k
+                    float* dst = p.partial + ((long)split * p.M + m) * p.N + n;
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    float b8[8];
-                    load8<T>(bias + n + j, b8);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[j + i] += b8[i];
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    continue;
                 }
-            }
-            if (p.bias2) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 b4 = *reinterpret_cast<const float4*>(p.bias2 + n + j);
-                    v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                }
-            }
-            if (p.geglu) {
-                float o[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_f(v[2 * j + 1]);
-                T* dst = C + m * p.ldc + n / 2;
-#pragma unroll
-                for (int j = 0; j < 16; j += 8) {
-                    float o8[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) o8[i] = o[j + i];
-                    store8<T>(dst + j, o8);
-                }
-            } else {
-                if (res) {
+                if (bias) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
-                        float r8[8];
-                        load8<T>(res + m * p.ldr + n + j, r8);
+                        float b8[8];
+                        load8<T>(bias + n + j, b8);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) v[j + i] += r8[i];
+                        for (int i = 0; i < 8; ++i) v[j + i] += b8[i];
                     }
                 }
-                T* dst = C + m * p.ldc + n;
+                if (p.bias2) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                    float o8[8];
+                    for (int j = 0; j < 32; j += 4) {
+                        float4 b4 = *reinterpret_cast<const float4*>(p.bias2 + n + j);
+                        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                    }
+                }
+                if (p.geglu) {
+                    float o[16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) o8[i] = v[j + i];
-                    store8<T>(dst + j, o8);
+                    for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_f(v[2 * j + 1]);
+                    T* dst = C + m * p.ldc + n / 2;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 8) {
+                        float o8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o8[i] = o[j + i];
+                        store8<T>(dst + j, o8);
+                    }
+                } else {
+                    if (res) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            float r8[8];
+                            load8<T>(res + m * p.ldr + n + j, r8);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[j + i] += r8[i];
+                        }
+                    }
+                    T* dst = C + m * p.ldc + n;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float o8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o8[i] = v[j + i];
+                        store8<T>(dst + j, o8);
+                    }
                 }
             }
+            tc_fence_before();  // TMEM reads of this accumulator are done
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, S::TMEM_COLS);
+}
+
+// split-K second pass: C = epilogue(sum_s partial[s]) in a fixed order (deterministic)
+template <typename T>
+__global__ void splitk_reduce_k(const float* __restrict__ partial, int splits, TcParams p) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;  // over M * N / 4
+    long total = p.M * p.N / 4;
+    if (i >= total) return;
+    long m = (i * 4) / p.N;
+    int n = (int)((i * 4) % p.N);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+        float4 v = *reinterpret_cast<const float4*>(partial + ((long)s * p.M + m) * p.N + n);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    const T* bias = reinterpret_cast<const T*>(p.bias);
+    const T* res = reinterpret_cast<const T*>(p.residual);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (bias) v[j] += to_f<T>(bias[n + j]);
+        if (p.bias2) v[j] += p.bias2[n + j];
+    }
+    T* C = reinterpret_cast<T*>(p.C);
+    if (p.geglu) {
+        C[m * p.ldc + n / 2] = from_f<T>(v[0] * gelu_f(v[1]));
+        C[m * p.ldc + n / 2 + 1] = from_f<T>(v[2] * gelu_f(v[3]));
+    } else {
+        if (res) {
+            float r4[4];
+            load4<T>(res + m * p.ldr + n, r4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] += r4[j];
+        }
+        store4<T>(C + m * p.ldc + n, v);
+    }
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
 }
 
 template <typename T, int BN, bool CONV>
@@ -236,12 +327,20 @@ void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, c
         CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_k<T, BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         configured = true;
     }
-    dim3 grid(cdiv(p.N, BN), cdiv(p.M, BM));
+    int items = p.tiles_m * p.tiles_n * p.splits;
+    int grid = items < num_sms() ? items : num_sms();
     gemm_tc_k<T, BN, CONV><<<grid, GT_THREADS, S::TOTAL, s>>>(tmA, tmB, p);
     KERNEL_CHECK();
+    if (p.partial) {
+        long total = p.M * p.N / 4;
+        splitk_reduce_k<T><<<cdiv(total, 256), 256, 0, s>>>(p.partial, p.splits, p);
+        KERNEL_CHECK();
+    }
 }
 
 }  // namespace
+
+size_t gemm_tc_splitk_workspace_bytes(long M, int N) { return (size_t)16 * M * N * sizeof(float); }
 
 bool gemm_tc_supported(const GemmArgs& a) {
     if (a.dtype != ETAI_F16 && a.dtype != ETAI_BF16) return false;
@@ -265,12 +364,14 @@ bool gemm_tc_supported(const GemmArgs& a) {
 void gemm_tc(const GemmArgs& a0, void* ws, size_t ws_bytes, cudaStream_t s) {
     ETAI_CHECK(gemm_tc_supported(a0), ETAI_ERR_UNSUPPORTED, "gemm_tc: unsupported problem");
     GemmArgs a = a0;
+    size_t ws_used = 0;
     if (a.conv && a.stride == 2) {
         // the three downsample convs (0.7% of UNet FLOPs): gather to [M, 9*Cin] once, then a dense GEMM
         size_t need = (size_t)a.M * 9 * a.Cin * 2;
         ETAI_CHECK(ws && ws_bytes >= need, ETAI_ERR_ARG, "gemm_tc: stride-2 conv needs an im2col workspace");
         im2col3x3(a.A, ws, a.B, a.H, a.Wd, a.Cin, 2, a.Ho, a.Wo, a.dtype, s);
         a.A = ws; a.conv = 0; a.lda = 9L * a.Cin; a.K = 9 * a.Cin;
+        ws_used = (need + 255) & ~size_t(255);
     }
     TcParams p;
     memset(&p, 0, sizeof(p));
@@ -278,6 +379,8 @@ void gemm_tc(const GemmArgs& a0, void* ws, size_t ws_bytes, cudaStream_t s) {
     p.M = a.M; p.N = a.N; p.ldc = a.ldc; p.ldr = a.ldr; p.geglu = a.geglu;
     p.fmt = a.dtype == ETAI_BF16 ? 1 : 0;
     const int BN = (a.N % 160 == 0) ? 160 : 128;
+    p.tiles_m = cdiv(a.M, BM);
+    p.tiles_n = cdiv(a.N, BN);
 
     CUtensorMap tmA, tmB;
     {
@@ -294,13 +397,30 @@ void gemm_tc(const GemmArgs& a0, void* ws, size_t ws_bytes, cudaStream_t s) {
         uint32_t box[4] = {(uint32_t)BK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
         tmA = make_tmap_16bit(a.A, a.dtype, 4, dims, str, box);
         p.cin_blocks = a.Cin / BK; p.num_kb = 9 * p.cin_blocks;
-        p.Himg = H; p.Wimg = W; p.bw = bw; p.bh = bh; p.bb = bb;
+        p.Himg = H; p.Wimg = W;
     } else {
         uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.M};
         uint64_t str[1] = {(uint64_t)a.lda * 2};
         uint32_t box[2] = {(uint32_t)BK, (uint32_t)BM};
         tmA = make_tmap_16bit(a.A, a.dtype, 2, dims, str, box);
         p.num_kb = a.K / BK;
+    }
+    // split-K for the low-resolution layers (few output tiles, K up to 23040): fill the SMs with K slices, fp32
+    // partials in the workspace, fixed-order reduction + epilogue in a second launch
+    p.splits = 1;
+    p.kb_per_split = p.num_kb;
+    const int tiles = p.tiles_m * p.tiles_n;
+    if (tiles * 2 <= num_sms() && p.num_kb >= 8 && ws != nullptr) {
+        int want = num_sms() / tiles;
+        if (want > 16) want = 16;
+        if (want > p.num_kb / 4) want = p.num_kb / 4;
+        size_t avail = ws_bytes > ws_used ? ws_bytes - ws_used : 0;
+        while (want > 1 && (size_t)want * a.M * a.N * sizeof(float) > avail) --want;
+        if (want > 1) {
+            p.kb_per_split = cdiv(p.num_kb, want);
+            p.splits = cdiv(p.num_kb, p.kb_per_split);
+            p.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ws_used);
+        }
     }
 #define LAUNCH(T)                                                            \
     do {                                                                     \

@@ -30,7 +30,8 @@ static GnPlan gn_plan(long HW, int C) {
     if (p.R < 1) p.R = 1;
     p.threads = (p.cvecs * p.R + 31) / 32 * 32;  // whole warps; the tail threads only help in the fold
     long rpc = 32;
-    while (cdiv(HW, rpc) > 32) rpc *= 2;  // <= 32 chunks: the apply kernel folds them with one lane per chunk
+    rpc = 8;
+    while (cdiv(HW, rpc) > 64) rpc *= 2;  // <= 64 chunks: the apply kernel folds them with two partials per lane
     if (rpc > HW) rpc = HW;
     p.rows_per_chunk = (int)rpc;
     p.chunks = cdiv(HW, rpc);
@@ -55,7 +56,17 @@ __global__ void gn_stats_k(const T* __restrict__ x, double* __restrict__ ws, lon
     for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
     const T* xb = x + (long)b * HW * C;
     if (r < R) {
-        for (long row = row0 + r; row < row1; row += R) {
+        long row = row0 + r;
+        for (; row + 3L * R < row1; row += 4L * R) {  // 4 independent 16-byte loads in flight per thread
+            float v[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) load8<T>(xb + (row + (long)u * R) * C + cv * 8, v[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s[j] += v[u][j]; ss[j] = fmaf(v[u][j], v[u][j], ss[j]); }
+        }
+        for (; row < row1; row += R) {
             float v[8];
             load8<T>(xb + row * C + cv * 8, v);
 #pragma unroll
@@ -122,19 +133,29 @@ __global__ void gn_apply_k(const T* __restrict__ x, T* __restrict__ y, const T* 
     int cvecs = C / 8, cpg = C / G;
     const T* xb = x + (long)b * HW * C;
     T* yb = y + (long)b * HW * C;
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < vecs_per_batch; i += (long)gridDim.x * blockDim.x) {
-        int c0 = (int)(i % cvecs) * 8;
-        float v[8], ga[8], be[8];
-        load8<T>(xb + i * 8, v);
-        load8<T>(gamma + c0, ga);
-        load8<T>(beta + c0, be);
+    const long stride = (long)gridDim.x * blockDim.x;
+    for (long i0 = blockIdx.x * (long)blockDim.x + threadIdx.x; i0 < vecs_per_batch; i0 += 2 * stride) {
+        float v[2][8];
+        const long i1 = i0 + stride;
+        const bool has1 = i1 < vecs_per_batch;
+        load8<T>(xb + i0 * 8, v[0]);
+        if (has1) load8<T>(xb + i1 * 8, v[1]);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            int g = (c0 + j) / cpg;
-            float o = (v[j] - s_mean[g]) * s_rstd[g] * ga[j] + be[j];
-            v[j] = SILU ? silu_f(o) : o;
+        for (int u = 0; u < 2; ++u) {
+            const long i = u == 0 ? i0 : i1;
+            if (u == 1 && !has1) break;
+            int c0 = (int)(i % cvecs) * 8;
+            float ga[8], be[8];
+            load8<T>(gamma + c0, ga);
+            load8<T>(beta + c0, be);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                int g = (c0 + j) / cpg;
+                float o = (v[u][j] - s_mean[g]) * s_rstd[g] * ga[j] + be[j];
+                v[u][j] = SILU ? silu_f(o) : o;
+            }
+            store8<T>(yb + i * 8, v[u]);
         }
-        store8<T>(yb + i * 8, v);
     }
 }
 
@@ -147,8 +168,8 @@ void groupnorm(const void* x, void* y, const void* gamma, const void* beta, int 
     size_t smem = (size_t)2 * p.R * C * sizeof(float);
     long vecs = HW * C / 8;
     // apply grid: ~4 CTAs per SM in total (each CTA re-derives mean/rstd from <= 32 chunk partials, then grid-strides)
-    int ablocks = (int)((vecs + 1023) / 1024);
-    int cap = (148 * 4 + B - 1) / B;
+    int ablocks = (int)((vecs + 511) / 512);
+    int cap = (148 * 6 + B - 1) / B;
     if (ablocks > cap) ablocks = cap;
     if (ablocks < 1) ablocks = 1;
     ETAI_DISPATCH_DTYPE(dtype, T, {

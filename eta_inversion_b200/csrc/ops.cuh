@@ -29,6 +29,7 @@ void gemm_simt(const GemmArgs& a, cudaStream_t s);
 void gemm_tc(const GemmArgs& a, void* ws, size_t ws_bytes, cudaStream_t s);
 bool gemm_tc_supported(const GemmArgs& a);
 
+
 // out[M,N] = act(x[M,K] (fp32) * W[N,K]^T (T) + bias) for tiny M (<=8); fp32 output. act: 0 none, 1 SiLU
 void skinny_linear(const float* x, const void* W, const void* bias, float* out, int M, int N, int K, int act,
                    int wdtype, cudaStream_t s);
@@ -81,8 +82,8 @@ void cross_attention_tc(const CrossAttnArgs& a, cudaStream_t s);    // tcgen05 (
 bool cross_attention_tc_supported(const CrossAttnArgs& a);
 
 // ---------------- data movement / elementwise -------------------------------------------------
-void nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int B, int C, long HW, cudaStream_t s);
-void nhwc_to_nchw(const void* in, int in_dtype, void* out, int out_dtype, int B, int C, long HW, cudaStream_t s);
+void nchw_to_nhwc(const void* in, int in_dtype, void* out, int out_dtype, int B, int C, int Cpad, long HW, cudaStream_t s);
+void nhwc_to_nchw(const void* in, int in_dtype, void* out, int out_dtype, int B, int C, int Cpad, long HW, cudaStream_t s);
 void convert(const void* in, int in_dtype, void* out, int out_dtype, long n, cudaStream_t s);
 void concat_channels(const void* a, int Ca, const void* b, int Cb, void* out, long rows, int dtype, cudaStream_t s);
 void upsample2x(const void* in, void* out, int B, int H, int W, int C, int dtype, cudaStream_t s);
@@ -92,7 +93,7 @@ void copy_rows(void* base, long row_elems, int src_row, int n_src, int dst_row, 
 void timestep_sincos(float t, float* out, int dim, cudaStream_t s);
 void add_inplace(void* y, const void* x, long n, int dtype, cudaStream_t s);
 // weight repack: OIHW -> O,(ky,kx),I ; optional GEGLU row interleave
-void pack_conv_weight(const float* oihw, void* out, int O, int I, int dtype, cudaStream_t s);
+void pack_conv_weight(const float* oihw, void* out, int O, int I, int Opad, int Ipad, int dtype, cudaStream_t s);
 void pack_geglu_weight(const float* w, const float* b, void* wout, void* bout, int N2, int K, int dtype, cudaStream_t s);
 
 // ---------------- scheduler -------------------------------------------------------------------

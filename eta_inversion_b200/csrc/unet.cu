@@ -174,13 +174,17 @@ struct etai_unet {
         }
         return l;
     }
-    Conv load_conv(const std::string& p, int cin, int cout) {
+    // cin_pad / cout_pad > 0: zero-pad to a tcgen05-friendly shape (conv_in 4 -> 64 input channels = one K block,
+    // conv_out 4 -> 32 output channels); the Conv then describes the padded problem.
+    Conv load_conv(const std::string& p, int cin, int cout, int cin_pad = 0, int cout_pad = 0) {
         Conv c;
-        c.cin = cin; c.cout = cout;
-        c.w = dmalloc((size_t)cout * 9 * cin * esz);
-        c.b = dmalloc(cout * esz);
+        c.cin = cin_pad > 0 ? cin_pad : cin;
+        c.cout = cout_pad > 0 ? cout_pad : cout;
+        c.w = dmalloc((size_t)c.cout * 9 * c.cin * esz);
+        c.b = dmalloc(c.cout * esz);
+        CUDA_CHECK(cudaMemset(c.b, 0, c.cout * esz));
         const float* s = staged(p + ".weight", {cout, cin, 3, 3});
-        pack_conv_weight(s, c.w, cout, cin, dt, 0);
+        pack_conv_weight(s, c.w, cout, cin, c.cout, c.cin, dt, 0);
         CUDA_CHECK(cudaStreamSynchronize(0));
         put(p + ".bias", {cout}, c.b);
         return c;
@@ -349,7 +353,7 @@ void etai_unet::build(const etai_tensor* weights, int n_weights) {
     kv_all.n = 2 * sum_c; kv_all.k = X;
     kv_all.w = dmalloc((size_t)2 * sum_c * X * esz);
 
-    conv_in = load_conv("conv_in", 4, c[0]);
+    conv_in = load_conv("conv_in", 4, c[0], tc ? 64 : 0, 0);
     time1 = load_lin("time_embedding.linear_1", temb, c[0], true);
     time2 = load_lin("time_embedding.linear_2", temb, temb, true);
     int cout = c[0];
@@ -381,7 +385,7 @@ void etai_unet::build(const etai_tensor* weights, int n_weights) {
         if (i < 3) up_samp[i] = load_conv("up_blocks." + std::to_string(i) + ".upsamplers.0.conv", cout, cout);
     }
     norm_out = load_norm("conv_norm_out", c[0]);
-    conv_out = load_conv("conv_out", c[0], 4);
+    conv_out = load_conv("conv_out", c[0], 4, 0, tc ? 32 : 0);
     ETAI_CHECK(temb_total == sum_res && kv_total == 2 * sum_c && n_tf == 16, ETAI_ERR_ARG, "architecture bookkeeping mismatch");
     CUDA_CHECK(cudaFree(stage));
     stage = nullptr;
@@ -505,10 +509,10 @@ void etai_unet::forward(const void* latent, float t, int io_dtype, int B, const 
         prof_end(ETAI_PROF_OTHER, e, 4, s);
     }
 
-    void* x = arena.alloc((size_t)B * H * W * 4 * esz);
+    void* x = arena.alloc((size_t)B * H * W * conv_in.cin * esz);
     if (!planning) {
         cudaEvent_t e = prof_begin(s);
-        nchw_to_nhwc(latent, io_dtype, x, dt, B, 4, (long)H * W, s);
+        nchw_to_nhwc(latent, io_dtype, x, dt, B, 4, conv_in.cin, (long)H * W, s);
         prof_end(ETAI_PROF_OTHER, e, 1, s);
     }
     void* h = conv3x3(x, B, H, W, conv_in, 1, nullptr, nullptr, s);
@@ -564,7 +568,7 @@ void etai_unet::forward(const void* latent, float t, int io_dtype, int B, const 
     void* o = conv3x3(a, B, H, W, conv_out, 1, nullptr, nullptr, s);
     if (!planning) {
         cudaEvent_t e = prof_begin(s);
-        nhwc_to_nchw(o, dt, eps_out, io_dtype, B, 4, (long)H * W, s);
+        nhwc_to_nchw(o, dt, eps_out, io_dtype, B, 4, conv_out.cout, (long)H * W, s);
         prof_end(ETAI_PROF_OTHER, e, 1, s);
     }
 }
@@ -599,7 +603,9 @@ void etai_unet::plan_workspace() {
             if (b > m) m = b;
             hw /= 4;
         }
-        tc_ws_bytes = m;
+        // + split-K partials: up to 16 fp32 copies of the largest low-resolution output (M <= max_batch*256, N <= c3)
+        size_t splitk = (size_t)16 * cfg.max_batch * 256 * c[3] * sizeof(float);
+        tc_ws_bytes = ((m + 255) & ~size_t(255)) + splitk;
         CUDA_CHECK(cudaMalloc(&tc_ws, tc_ws_bytes));
     }
     workspace_bytes += (size_t)ctx_m * (kv_total + cfg.cross_dim) * esz + gws + tc_ws_bytes;

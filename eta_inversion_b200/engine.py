@@ -226,7 +226,9 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias=None, residual=None, s
     Co = w_packed.shape[0]
     Ho, Wo = (H - 1) // stride + 1, (Wd - 1) // stride + 1
     out = torch.empty((B, Ho, Wo, Co), dtype=x.dtype, device=x.device)
-    ws = torch.empty((B * Ho * Wo * 9 * Ci,), dtype=x.dtype, device=x.device) if stride == 2 else None
+    # workspace: im2col for stride 2 plus room for split-K partials of small problems
+    ws_elems = (B * Ho * Wo * 9 * Ci if stride == 2 else 0) + (16 * B * Ho * Wo * Co * 2 if B * Ho * Wo <= 2048 else 0)
+    ws = torch.empty((max(ws_elems, 1) + 256,), dtype=x.dtype, device=x.device)
     check(_lib.load().etai_conv3x3(ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(out), B, H, Wd, Ci, Co, stride,
                                    dtype_code(x.dtype), math_mode, ptr(ws), 0 if ws is None else ws.numel() * ws.element_size(),
                                    stream_ptr()))
