@@ -1,6 +1,8 @@
 // tcgen05 cross-attention over the 77-token text context with prompt-to-prompt control fused in (16-bit engine).
 //
-// CTA = 128 query rows x one group (a plain UNet row, or a (base, target) PtP pair), looping over the heads.
+// CTA = 128 query rows x one group (a plain UNet row, or a (base, target) PtP pair) x one head; grid (q tiles, groups,
+// heads) so that even the 8x8 / 16x16 layers spread over the SMs.  Per-head store partials go to a workspace and are
+// folded into the accumulators in head order by a second tiny launch (deterministic, no atomics).
 // Per (head, row):   S = Q K^T            UMMA 128 x 80 x d      (K tile: 77 keys, TMA zero-fills 77..79 and the d tail)
 //                    softmax per thread   (one query row per thread, 77 probabilities in registers, fp32)
 //   target row only: R = P_base Mapper    UMMA 128 x 80 x 80     (P_base is still in smem from the base pass)
@@ -31,7 +33,9 @@ struct XParams {
     int n_groups;
     CrossGroup groups[ETAI_MAX_ROWS];
     const float *mapper, *blend_a, *equalizer, *alpha_step;
-    float* store;
+    float* store;        // accumulators [slots][N][L] (used by the reduce launch)
+    float* store_part;   // per-head partials [heads][slots][N][L]
+    int n_slots;
     int fmt;
 };
 
@@ -82,10 +86,14 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 }
 
 template <typename T, int ATOMS, int STAGES>
-__global__ void __launch_bounds__(XT_THREADS, 1)
+__global__ void __launch_bounds__(XT_THREADS, ATOMS == 1 ? 2 : 1)
 cross_attn_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ XParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmM,
+                const __grid_constant__ XParams p) {
     constexpr int STAGE_BYTES = ATOMS * (QATOM + 2 * KATOM);
+    // TMEM columns: S (80) | R (80) | O (d_pad).  d = 40 fits 256 columns (two CTAs per SM), larger heads take 512
+    constexpr int TMEM_COLS = ATOMS == 1 ? 256 : 512;
+    constexpr int R_COL = ATOMS == 1 ? 96 : 128, O_COL = ATOMS == 1 ? 192 : 256;
     constexpr int PA_OFF = STAGES * STAGE_BYTES;       // P (A operand): 2 atoms of [128 x 128 B]
     constexpr int MAP_OFF = PA_OFF + 2 * QATOM;        // Mapper^T (B operand, K-major): 2 atoms of [80 x 128 B]
     constexpr int BAR_OFF = MAP_OFF + 2 * KATOM;
@@ -98,14 +106,16 @@ cross_attn_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* s_full = kv_empty + STAGES;
     uint64_t* p_ready = s_full + 1;
     uint64_t* o_full = p_ready + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+    uint64_t* map_full = o_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(map_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const CrossGroup g = p.groups[blockIdx.y];
     const int q0 = blockIdx.x * 128;
     const int nrows = g.tgt >= 0 ? 2 : 1;
     const bool edit = g.tgt >= 0 && p.mapper != nullptr;
-    const int iters = p.heads * nrows;
+    const int iters = nrows;
+    const int head = blockIdx.z;
     const int ksteps = (D + 15) / 16;
 
     if (warp == 0 && lane == 0) {
@@ -114,33 +124,25 @@ cross_attn_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_init(s_full, 1);
         mbar_init(p_ready, 128);
         mbar_init(o_full, 1);
+        mbar_init(map_full, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
-    if (edit) {
-        // Mapper^T as a K-major / 128B-swizzled B operand: row n, K index w  <-  mapper[w][n]
-        unsigned char* mp = smem + MAP_OFF;
-        for (int i = threadIdx.x; i < 2 * KATOM / 16; i += XT_THREADS) reinterpret_cast<uint4*>(mp)[i] = make_uint4(0, 0, 0, 0);
-        __syncthreads();
-        const float* M = p.mapper + (long)g.pair * p.L * p.L;
-        for (int i = threadIdx.x; i < p.L * p.L; i += XT_THREADS) {
-            int w = i / p.L, n = i % p.L;
-            T val = from_f<T>(M[i]);
-            int chunk = ((w & 63) >> 3) ^ (n & 7);
-            *reinterpret_cast<T*>(mp + (w >> 6) * KATOM + n * 128 + chunk * 16 + (w & 7) * 2) = val;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
+    if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_r = tmem_base + 128, tmem_o = tmem_base + 256;
+    const uint32_t tmem_r = tmem_base + R_COL, tmem_o = tmem_base + O_COL;
 
     if (warp == 0) {
         if (lane == 0) {
+            if (edit) {  // Mapper^T (16-bit, [80 n][128 w] zero padded, prepared once per forward): B operand of R = P_base M
+                mbar_expect_tx(map_full, 2 * KATOM);
+                tma_load_3d(smem + MAP_OFF, &tmM, map_full, 0, 0, g.pair);
+                tma_load_3d(smem + MAP_OFF + KATOM, &tmM, map_full, 64, 0, g.pair);
+            }
             for (int it = 0; it < iters; ++it) {
-                int head = it / nrows, row = (it % nrows) == 0 ? g.base : g.tgt;
+                int row = it == 0 ? g.base : g.tgt;
                 int s = it % STAGES;
                 mbar_wait(&kv_empty[s], ((it / STAGES) & 1) ^ 1);
                 mbar_expect_tx(&kv_full[s], STAGE_BYTES);
@@ -170,6 +172,8 @@ cross_attn_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                              make_smem_desc_sw128(ka + (k >> 2) * KATOM + ko), idesc_s, k != 0);
                 }
                 if (edit && is_tgt) {
+                    mbar_wait(map_full, 0);
+                    tc_fence_after();
 #pragma unroll
                     for (int k = 0; k < LP / 16; ++k) {
                         uint32_t ko = (uint32_t)(k & 3) * 32;
@@ -201,8 +205,7 @@ cross_attn_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float* eq = edit ? p.equalizer + g.pair * p.L : nullptr;
         const float* ba = edit ? p.blend_a + g.pair * p.L : nullptr;
         for (int it = 0; it < iters; ++it) {
-            const int head = it / nrows;
-            const bool is_tgt = (it % nrows) == 1;
+            const bool is_tgt = it == 1;
             const int row = is_tgt ? g.tgt : g.base;
             mbar_wait(s_full, it & 1);
             tc_fence_after();
@@ -238,11 +241,11 @@ cross_attn_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 }
             }
             const int slot = is_tgt ? g.store_tgt : g.store_base;
-            if (p.store && slot >= 0 && q_ok) {
-                float* acc = p.store + ((long)slot * p.N + q) * p.L;  // single owner thread, heads in order
+            if (p.store_part && slot >= 0 && q_ok) {  // per-head partial; folded in head order by store_reduce_k
+                float* part = p.store_part + (((long)head * p.n_slots + slot) * p.N + q) * p.L;
 #pragma unroll
                 for (int i = 0; i < LP; ++i)
-                    if (i < p.L) acc[i] += pr[i];
+                    if (i < p.L) part[i] = pr[i];
             }
             // P' -> shared memory as the A operand (K-major, 128B swizzle): 80 values = atom 0 (64) + atom 1 (16)
 #pragma unroll
@@ -275,18 +278,27 @@ cross_attn_tc_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+__global__ void store_reduce_k(float* __restrict__ acc, const float* __restrict__ part, int heads, long n) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a = acc[i];
+    for (int h = 0; h < heads; ++h) a += part[(long)h * n + i];
+    acc[i] = a;
 }
 
 template <typename T, int ATOMS, int STAGES>
-void launch_x(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const XParams& p, dim3 grid, cudaStream_t s) {
+void launch_x(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const CUtensorMap& m, const XParams& p, dim3 grid,
+              cudaStream_t s) {
     constexpr int SMEM = STAGES * ATOMS * (QATOM + 2 * KATOM) + 2 * QATOM + 2 * KATOM + 256 + 1024;
     static bool configured = false;
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(cross_attn_tc_k<T, ATOMS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         configured = true;
     }
-    cross_attn_tc_k<T, ATOMS, STAGES><<<grid, XT_THREADS, SMEM, s>>>(q, k, v, p);
+    cross_attn_tc_k<T, ATOMS, STAGES><<<grid, XT_THREADS, SMEM, s>>>(q, k, v, m, p);
     KERNEL_CHECK();
 }
 
@@ -297,40 +309,81 @@ CUtensorMap tmap4(const void* base, int dtype, int d, int heads, int N, int B, l
     return make_tmap_16bit(base, dtype, 4, dims, str, box);
 }
 
+// mapper fp32 [P][L][L] (row w, column n)  ->  16-bit [P][80 n][128 w], zero padded: K-major B operand for R = P_base M
+template <typename T>
+__global__ void prep_mapper_k(const float* __restrict__ m, T* __restrict__ out, int P, int L) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P * LP * 128) return;
+    int w = i % 128, n = (i / 128) % LP, p = i / (128 * LP);
+    out[i] = (w < L && n < L) ? from_f<T>(m[((long)p * L + w) * L + n]) : from_f<T>(0.f);
+}
+
 }  // namespace
+
+size_t cross_attention_tc_mapper_bytes(int pairs) { return (size_t)pairs * LP * 128 * 2; }
+
+void cross_attention_tc_prep_mapper(const float* mapper, void* map16, int pairs, int L, int dtype, cudaStream_t s) {
+    int n = pairs * LP * 128;
+    if (dtype == ETAI_F16) prep_mapper_k<__half><<<cdiv(n, 256), 256, 0, s>>>(mapper, (__half*)map16, pairs, L);
+    else prep_mapper_k<__nv_bfloat16><<<cdiv(n, 256), 256, 0, s>>>(mapper, (__nv_bfloat16*)map16, pairs, L);
+    KERNEL_CHECK();
+}
 
 bool cross_attention_tc_supported(const CrossAttnArgs& a) {
     if (a.dtype != ETAI_F16 && a.dtype != ETAI_BF16) return false;
     if (a.d != 40 && a.d != 80 && a.d != 160) return false;
     if (a.L > 80 || a.L < 1 || a.ldq % 8 || a.ldkv % 8 || a.ldo % 8 || a.koff % 8 || a.voff % 8) return false;
+    if (a.mapper && !a.map16) return false;
+    if (a.store && !a.store_part) return false;
     return true;
 }
 
-void cross_attention_tc(const CrossAttnArgs& a, cudaStream_t s) {
+int cross_attention_tc(const CrossAttnArgs& a, cudaStream_t s) {
     ETAI_CHECK(cross_attention_tc_supported(a), ETAI_ERR_UNSUPPORTED, "cross_attention_tc: unsupported problem");
     XParams p;
     memset(&p, 0, sizeof(p));
     p.out = a.out; p.N = a.N; p.L = a.L; p.heads = a.heads; p.d = a.d; p.ldo = a.ldo;
     p.scale_log2e = a.scale * 1.4426950408889634f;
     p.n_groups = a.n_groups;
-    for (int i = 0; i < a.n_groups; ++i) p.groups[i] = a.groups[i];
+    int n_slots = 0;
+    for (int i = 0; i < a.n_groups; ++i) {
+        p.groups[i] = a.groups[i];
+        if (a.groups[i].store_base + 1 > n_slots) n_slots = a.groups[i].store_base + 1;
+        if (a.groups[i].store_tgt + 1 > n_slots) n_slots = a.groups[i].store_tgt + 1;
+    }
     p.mapper = a.mapper; p.blend_a = a.blend_a; p.equalizer = a.equalizer; p.alpha_step = a.alpha_step;
     p.store = a.store;
+    p.store_part = (a.store && n_slots > 0) ? a.store_part : nullptr;
+    p.n_slots = n_slots;
     p.fmt = a.dtype == ETAI_BF16 ? 1 : 0;
     const char* kv = reinterpret_cast<const char*>(a.kv);
     CUtensorMap tq = tmap4(a.q, a.dtype, a.d, a.heads, a.N, a.B, a.ldq, 128);
     CUtensorMap tk = tmap4(kv + (size_t)a.koff * 2, a.dtype, a.d, a.heads, a.L, a.B, a.ldkv, 80);
     CUtensorMap tv = tmap4(kv + (size_t)a.voff * 2, a.dtype, a.d, a.heads, a.L, a.B, a.ldkv, 80);
-    dim3 grid(cdiv(a.N, 128), a.n_groups);
-#define LAUNCH(T)                                                          \
-    do {                                                                   \
-        if (a.d == 40) launch_x<T, 1, 2>(tq, tk, tv, p, grid, s);          \
-        else if (a.d == 80) launch_x<T, 2, 2>(tq, tk, tv, p, grid, s);     \
-        else launch_x<T, 3, 1>(tq, tk, tv, p, grid, s);                    \
+    CUtensorMap tm = tq;  // placeholder when no edit is active (never dereferenced)
+    if (a.mapper) {
+        uint64_t dims[3] = {128, (uint64_t)LP, (uint64_t)ETAI_MAX_PAIRS};
+        uint64_t str[2] = {128 * 2, (uint64_t)128 * 2 * LP};
+        uint32_t box[3] = {64, (uint32_t)LP, 1};
+        tm = make_tmap_16bit(a.map16, a.dtype, 3, dims, str, box);
+    }
+    dim3 grid(cdiv(a.N, 128), a.n_groups, a.heads);
+#define LAUNCH(T)                                                              \
+    do {                                                                       \
+        if (a.d == 40) launch_x<T, 1, 1>(tq, tk, tv, tm, p, grid, s);          \
+        else if (a.d == 80) launch_x<T, 2, 1>(tq, tk, tv, tm, p, grid, s);     \
+        else launch_x<T, 3, 1>(tq, tk, tv, tm, p, grid, s);                    \
     } while (0)
     if (a.dtype == ETAI_F16) LAUNCH(__half);
     else LAUNCH(__nv_bfloat16);
 #undef LAUNCH
+    if (p.store_part) {
+        long n = (long)n_slots * a.N * a.L;
+        store_reduce_k<<<cdiv(n, 256), 256, 0, s>>>(a.store, a.store_part, a.heads, n);
+        KERNEL_CHECK();
+        return 2;
+    }
+    return 1;
 }
 
 }  // namespace etai

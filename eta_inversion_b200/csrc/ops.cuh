@@ -75,10 +75,16 @@ struct CrossAttnArgs {
     CrossGroup groups[ETAI_MAX_ROWS];
     const float *mapper, *blend_a, *equalizer, *alpha_step;  // per pair tables or null (no edit)
     float* store;  // [slots][N][L] fp32 accumulators or null
+    // tcgen05 path only: 16-bit transposed/padded mapper prepared by cross_attention_tc_prep_mapper, and a
+    // [heads][slots][N][L] fp32 workspace for per-head store partials
+    const void* map16;
+    float* store_part;
     int dtype;
 };
 void cross_attention(const CrossAttnArgs& a, cudaStream_t s);       // SIMT, fp32 math (parity path)
-void cross_attention_tc(const CrossAttnArgs& a, cudaStream_t s);    // tcgen05 (16-bit engine)
+int cross_attention_tc(const CrossAttnArgs& a, cudaStream_t s);     // tcgen05 (16-bit engine); returns #launches
+size_t cross_attention_tc_mapper_bytes(int pairs);
+void cross_attention_tc_prep_mapper(const float* mapper, void* map16, int pairs, int L, int dtype, cudaStream_t s);
 bool cross_attention_tc_supported(const CrossAttnArgs& a);
 
 // ---------------- data movement / elementwise -------------------------------------------------

@@ -80,6 +80,9 @@ struct etai_unet {
     void* gn_ws = nullptr;
     void* tc_ws = nullptr;
     size_t tc_ws_bytes = 0;
+    void* map16_buf = nullptr;      // prompt-to-prompt mapper in the tcgen05 B-operand form (per forward)
+    float* store_part_buf = nullptr;  // per-head attention-store partials
+    bool map16_ready = false;
     size_t workspace_bytes = 0;
 
     // ---- instrumentation: launch counter (always) + per-category CUDA-event timing (opt-in) -----
@@ -463,9 +466,12 @@ void* etai_unet::transformer(const void* x, int B, int H, int W, const Tfm& t, c
             if (!used[r]) a.groups[ng++] = CrossGroup{r, -1, 0, slot_of[r], -1};
         a.n_groups = ng;
         cudaEvent_t e = prof_begin(s);
-        if (tc && cross_attention_tc_supported(a)) cross_attention_tc(a, s);
+        int nl = 1;
+        a.map16 = (a.mapper && map16_ready) ? map16_buf : nullptr;
+        a.store_part = store_part_buf;
+        if (tc && cross_attention_tc_supported(a)) nl = cross_attention_tc(a, s);
         else cross_attention(a, s);
-        prof_end(ETAI_PROF_CROSS_ATTN, e, 1, s);
+        prof_end(ETAI_PROF_CROSS_ATTN, e, nl, s);
     }
     h = linear(co, M, t.o2, h, s);
     // ---- feed forward (GEGLU) ----
@@ -509,6 +515,13 @@ void etai_unet::forward(const void* latent, float t, int io_dtype, int B, const 
         prof_end(ETAI_PROF_OTHER, e, 4, s);
     }
 
+    map16_ready = false;
+    if (!planning && tc && ctrl && (ctrl->flags & ETAI_CTRL_CROSS_EDIT)) {
+        cudaEvent_t e = prof_begin(s);
+        cross_attention_tc_prep_mapper(ctrl->mapper, map16_buf, ctrl->n_pairs, cfg.ctx_len, dt, s);
+        prof_end(ETAI_PROF_OTHER, e, 1, s);
+        map16_ready = true;
+    }
     void* x = arena.alloc((size_t)B * H * W * conv_in.cin * esz);
     if (!planning) {
         cudaEvent_t e = prof_begin(s);
@@ -607,6 +620,11 @@ void etai_unet::plan_workspace() {
         size_t splitk = (size_t)16 * cfg.max_batch * 256 * c[3] * sizeof(float);
         tc_ws_bytes = ((m + 255) & ~size_t(255)) + splitk;
         CUDA_CHECK(cudaMalloc(&tc_ws, tc_ws_bytes));
+        CUDA_CHECK(cudaMalloc(&map16_buf, cross_attention_tc_mapper_bytes(ETAI_MAX_PAIRS)));
+        CUDA_CHECK(cudaMemset(map16_buf, 0, cross_attention_tc_mapper_bytes(ETAI_MAX_PAIRS)));
+        size_t sp = (size_t)cfg.heads * cfg.max_batch * 1024 * cfg.ctx_len * sizeof(float);  // store maps up to 32x32
+        CUDA_CHECK(cudaMalloc((void**)&store_part_buf, sp));
+        workspace_bytes += sp;
     }
     workspace_bytes += (size_t)ctx_m * (kv_total + cfg.cross_dim) * esz + gws + tc_ws_bytes;
 }
@@ -679,6 +697,8 @@ int etai_unet_destroy(etai_unet* h) {
     if (h->tbuf) cudaFree(h->tbuf);
     if (h->gn_ws) cudaFree(h->gn_ws);
     if (h->tc_ws) cudaFree(h->tc_ws);
+    if (h->map16_buf) cudaFree(h->map16_buf);
+    if (h->store_part_buf) cudaFree(h->store_part_buf);
     if (h->stage) cudaFree(h->stage);
     delete h;
     return ETAI_OK;
