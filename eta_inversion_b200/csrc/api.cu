@@ -59,7 +59,9 @@ int etai_groupnorm(const void* x, void* y, const void* gamma, const void* beta, 
     ETAI_API_BEGIN
     ETAI_CHECK(x && y && gamma && beta && B >= 1 && HW >= 1, ETAI_ERR_ARG, "groupnorm: null/empty argument");
     ETAI_CHECK((size_t)workspace_bytes >= groupnorm_workspace_bytes(B, HW, C, groups), ETAI_ERR_ARG,
-               "groupnorm: workspace too small (need B*256*groups*16 bytes)");
+               "groupnorm: workspace too small (need 33024 + B*256*groups*16 bytes)");
+    CUDA_CHECK(cudaMemsetAsync(reinterpret_cast<char*>(workspace) + groupnorm_ticket_offset(B, groups), 0, 64 * sizeof(int),
+                               (cudaStream_t)stream));
     groupnorm(x, y, gamma, beta, B, HW, C, groups, eps, silu != 0, dtype, workspace, (cudaStream_t)stream);
     ETAI_API_END
 }

@@ -281,6 +281,292 @@ void launch_attn(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& 
     KERNEL_CHECK();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Two-query-tile ("ping-pong") variant for the large layers (d = 40 / 80, N >= 256): one CTA owns 256 query rows as
+// two 128-row tiles, each with its own softmax warpgroup, S accumulator, P buffer and O accumulator.  The single MMA
+// thread alternates between the tiles, so the tensor core computes S/PV of one tile while the other tile's warpgroup
+// is in its softmax, and every K/V tile is fetched once for 256 queries.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int AT2_THREADS = 32 * 10;  // warp 0 TMA, warp 1 MMA, warps 2..5 softmax tile 0, warps 6..9 softmax tile 1
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <typename T, int ATOMS, int STAGES>
+__global__ void __launch_bounds__(AT2_THREADS, 1)
+attn_tc2_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AtParams p) {
+    constexpr int OP_BYTES = ATOMS * ATOM_BYTES;
+    constexpr int KV_BYTES = 2 * OP_BYTES;
+    constexpr int KV_OFF = 2 * OP_BYTES;                      // after Q0, Q1
+    constexpr int P_OFF = KV_OFF + STAGES * KV_BYTES;         // P0, P1: 2 atoms each
+    constexpr int BAR_OFF = P_OFF + 4 * ATOM_BYTES;
+    constexpr int DPAD = ATOMS == 1 ? 48 : 80;
+    constexpr int D = ATOMS == 1 ? 40 : 80;
+    constexpr int O_STRIDE = ATOMS == 1 ? 64 : 96;            // TMEM columns between O0 and O1 (at column 256)
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+    uint64_t* kv_full = q_full + 1;
+    uint64_t* kv_empty = kv_full + STAGES;
+    uint64_t* s_full = kv_empty + STAGES;  // [2] per query tile
+    uint64_t* p_full = s_full + 2;         // [2]
+    uint64_t* o_full = p_full + 2;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 256, head = blockIdx.y, row = blockIdx.z;
+    const int ntiles = (p.Nk + BKV - 1) / BKV;
+    constexpr int ksteps = (D + 15) / 16;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g], 1); mbar_init(&p_full[g], 128); mbar_init(&o_full[g], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(q_full, 2 * OP_BYTES);
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+#pragma unroll
+                for (int a = 0; a < ATOMS; ++a)
+                    tma_load_4d(smem + g * OP_BYTES + a * ATOM_BYTES, &tmQ, q_full, a * 64, head, q0 + g * 128, p.map.q[row]);
+            for (int j = 0; j < ntiles; ++j) {
+                int s = j % STAGES;
+                mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
+                mbar_expect_tx(&kv_full[s], KV_BYTES);
+                unsigned char* kb = smem + KV_OFF + s * KV_BYTES;
+#pragma unroll
+                for (int a = 0; a < ATOMS; ++a) {
+                    tma_load_4d(kb + a * ATOM_BYTES, &tmK, &kv_full[s], a * 64, head, j * BKV, p.map.k[row]);
+                    tma_load_4d(kb + OP_BYTES + a * ATOM_BYTES, &tmV, &kv_full[s], a * 64, head, j * BKV, p.map.v[row]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc_f16(p.fmt, BQ, BKV);
+            const uint32_t idesc_o = make_idesc_f16_bmn(p.fmt, BQ, DPAD);
+            auto issue_s = [&](int g, int j) {
+                int s = j % STAGES;
+                uint32_t q_addr = smem_u32(smem + g * OP_BYTES);
+                uint32_t k_addr = smem_u32(smem + KV_OFF + s * KV_BYTES);
+#pragma unroll
+                for (int k = 0; k < ksteps; ++k) {
+                    uint32_t off = (uint32_t)(k >> 2) * ATOM_BYTES + (uint32_t)(k & 3) * 32;
+                    umma_f16(tmem_base + (uint32_t)g * 128, make_smem_desc_sw128(q_addr + off),
+                             make_smem_desc_sw128(k_addr + off), idesc_s, k != 0);
+                }
+                umma_commit(&s_full[g]);
+            };
+            auto issue_o = [&](int g, int j) {
+                int s = j % STAGES;
+                mbar_wait(&p_full[g], j & 1);
+                tc_fence_after();
+                uint32_t p_addr = smem_u32(smem + P_OFF + g * 2 * ATOM_BYTES);
+                uint32_t v_addr = smem_u32(smem + KV_OFF + s * KV_BYTES + OP_BYTES);
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k) {
+                    uint32_t a_off = (uint32_t)(k >> 2) * ATOM_BYTES + (uint32_t)(k & 3) * 32;
+                    umma_f16(tmem_base + 256 + (uint32_t)g * O_STRIDE, make_smem_desc_sw128(p_addr + a_off),
+                             make_smem_desc_mn_sw128(v_addr + (uint32_t)k * 16 * 128, ATOM_BYTES), idesc_o, k != 0);
+                }
+                if (g == 1) umma_commit(&kv_empty[s]);  // both query tiles are done with K_j / V_j
+                umma_commit(&o_full[g]);
+            };
+            auto wait_kv = [&](int j) {
+                mbar_wait(&kv_full[j % STAGES], (j / STAGES) & 1);
+                tc_fence_after();
+            };
+            mbar_wait(q_full, 0);
+            wait_kv(0);
+            issue_s(0, 0);
+            issue_s(1, 0);
+            for (int j = 0; j < ntiles; ++j) {
+                const bool more = j + 1 < ntiles;
+                if (STAGES >= 2) {
+                    issue_o(0, j);
+                    if (more) { wait_kv(j + 1); issue_s(0, j + 1); }
+                    issue_o(1, j);
+                    if (more) issue_s(1, j + 1);
+                } else {
+                    issue_o(0, j);
+                    issue_o(1, j);
+                    if (more) { wait_kv(j + 1); issue_s(0, j + 1); issue_s(1, j + 1); }
+                }
+            }
+        }
+    } else {
+        const int g = (warp - 2) >> 2;      // query tile / softmax warpgroup
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const uint32_t s_addr = tmem_base + (uint32_t)g * 128 + lane_addr;
+        const uint32_t o_addr = tmem_base + 256 + (uint32_t)g * O_STRIDE + lane_addr;
+        unsigned char* p_row = smem + P_OFF + g * 2 * ATOM_BYTES + r * 128;
+        float o_acc[DPAD];
+#pragma unroll
+        for (int i = 0; i < DPAD; ++i) o_acc[i] = 0.f;
+        float m_run = -INFINITY, l_run = 0.f, alpha_pending = 1.f;
+
+        auto fold_o = [&](int j) {
+            mbar_wait(&o_full[g], j & 1);
+            tc_fence_after();
+            constexpr int N32 = DPAD / 32;
+#pragma unroll
+            for (int b = 0; b < N32; ++b) {
+                float v[32];
+                tmem_ld32(o_addr + b * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o_acc[b * 32 + i] = fmaf(o_acc[b * 32 + i], alpha_pending, v[i]);
+            }
+            {
+                uint32_t rr[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]),
+                      "=r"(rr[7]), "=r"(rr[8]), "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]),
+                      "=r"(rr[14]), "=r"(rr[15])
+                    : "r"(o_addr + N32 * 32)
+                    : "memory");
+                tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    o_acc[N32 * 32 + i] = fmaf(o_acc[N32 * 32 + i], alpha_pending, __uint_as_float(rr[i]));
+            }
+        };
+
+        for (int j = 0; j < ntiles; ++j) {
+            mbar_wait(&s_full[g], j & 1);
+            tc_fence_after();
+            const int kbase = j * BKV;
+            const bool full_tile = kbase + BKV <= p.Nk;
+            // pass 1: row max (two batches of 64 columns, one TMEM wait each)
+            float mx = -INFINITY;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t a[32], b[32];
+                tmem_ld32_nowait(s_addr + h * 64, a);
+                tmem_ld32_nowait(s_addr + h * 64 + 32, b);
+                tmem_wait_ld();
+                if (full_tile) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(__uint_as_float(a[i]), __uint_as_float(b[i])));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (kbase + h * 64 + i < p.Nk) mx = fmaxf(mx, __uint_as_float(a[i]));
+                        if (kbase + h * 64 + 32 + i < p.Nk) mx = fmaxf(mx, __uint_as_float(b[i]));
+                    }
+                }
+            }
+            const float m_new = fmaxf(m_run, mx);
+            const float alpha = ex2_approx((m_run - m_new) * p.scale_log2e);
+            const float mb = m_new * p.scale_log2e;
+            if (j > 0) fold_o(j - 1);
+            alpha_pending = alpha;
+            float sum = 0.f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t a[32], b[32];
+                tmem_ld32_nowait(s_addr + h * 64, a);
+                tmem_ld32_nowait(s_addr + h * 64 + 32, b);
+                tmem_wait_ld();
+                unsigned char* atom = p_row + h * ATOM_BYTES;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t packed[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float s0 = __uint_as_float(half == 0 ? a[i] : b[i]);
+                        float s1 = __uint_as_float(half == 0 ? a[i + 1] : b[i + 1]);
+                        float p0 = ex2_approx(fmaf(s0, p.scale_log2e, -mb));
+                        float p1 = ex2_approx(fmaf(s1, p.scale_log2e, -mb));
+                        if (!full_tile) {
+                            if (kbase + h * 64 + half * 32 + i >= p.Nk) p0 = 0.f;
+                            if (kbase + h * 64 + half * 32 + i + 1 >= p.Nk) p1 = 0.f;
+                        }
+                        sum += p0 + p1;
+                        if constexpr (std::is_same<T, __half>::value) {
+                            __half2 hh = __floats2half2_rn(p0, p1);
+                            packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                        } else {
+                            __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+                            packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        int chunk = (half * 4 + q) ^ (r & 7);
+                        *reinterpret_cast<uint4*>(atom + chunk * 16) =
+                            make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+                    }
+                }
+            }
+            l_run = l_run * alpha + sum;
+            m_run = m_new;
+            tc_fence_before();
+            fence_async_smem();
+            mbar_arrive(&p_full[g]);
+        }
+        fold_o(ntiles - 1);
+        const int q = q0 + g * 128 + r;
+        if (q < p.Nq) {
+            const float inv = 1.f / l_run;
+            T* dst = reinterpret_cast<T*>(p.out) + ((long)row * p.Nq + q) * p.ldo + head * p.d;
+#pragma unroll
+            for (int c = 0; c < D; c += 8) {
+                float o8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o8[i] = o_acc[c + i] * inv;
+                store8<T>(dst + c, o8);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <typename T, int ATOMS, int STAGES>
+void launch_attn2(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AtParams& p, dim3 grid, cudaStream_t s) {
+    constexpr int SMEM = 2 * ATOMS * ATOM_BYTES + STAGES * 2 * ATOMS * ATOM_BYTES + 4 * ATOM_BYTES + 256 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(attn_tc2_k<T, ATOMS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
+    attn_tc2_k<T, ATOMS, STAGES><<<grid, AT2_THREADS, SMEM, s>>>(q, k, v, p);
+    KERNEL_CHECK();
+}
+
 CUtensorMap head_tmap(const void* base, int dtype, int d, int heads, int N, int B, long ld) {
     uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)N, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)d * 2, (uint64_t)ld * 2, (uint64_t)ld * 2 * N};
@@ -311,9 +597,13 @@ void attention_tc(const SelfAttnArgs& a, cudaStream_t s) {
     CUtensorMap tk = head_tmap(a.k, a.dtype, a.d, a.heads, a.Nk, a.B, a.ldk);
     CUtensorMap tv = head_tmap(a.v, a.dtype, a.d, a.heads, a.Nk, a.B, a.ldv);
     dim3 grid(cdiv(a.Nq, BQ), a.heads, a.B);
+    const bool two = a.d != 160 && a.Nq >= 256;  // ping-pong kernel: 256 query rows per CTA
+    if (two) grid.x = cdiv(a.Nq, 256);
 #define LAUNCH(T)                                                              \
     do {                                                                       \
-        if (a.d == 40) launch_attn<T, 1, 2>(tq, tk, tv, p, grid, s);           \
+        if (two && a.d == 40) launch_attn2<T, 1, 2>(tq, tk, tv, p, grid, s);   \
+        else if (two) launch_attn2<T, 2, 1>(tq, tk, tv, p, grid, s);           \
+        else if (a.d == 40) launch_attn<T, 1, 2>(tq, tk, tv, p, grid, s);      \
         else if (a.d == 80) launch_attn<T, 2, 2>(tq, tk, tv, p, grid, s);      \
         else launch_attn<T, 3, 1>(tq, tk, tv, p, grid, s);                     \
     } while (0)

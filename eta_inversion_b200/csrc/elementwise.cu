@@ -155,16 +155,17 @@ void copy_rows(void* base, long row_elems, int src_row, int n_src, int dst_row, 
 // ---------------------------------------------------------------------------------------------
 // time embedding: [cos(t f_i), sin(t f_i)], f_i = exp(-ln(1e4) i / half)  (flip_sin_to_cos=True, shift 0)
 // ---------------------------------------------------------------------------------------------
-__global__ void timestep_sincos_k(float t, float* out, int half) {
+__global__ void timestep_sincos_k(const float* __restrict__ t_dev, float* out, int half) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= half) return;
+    const float t = *t_dev;  // read from device memory so a captured CUDA graph can be replayed for any timestep
     float f = expf(-9.210340371976184f * (float)i / (float)half);
     float a = t * f;
     out[i] = cosf(a);
     out[half + i] = sinf(a);
 }
-void timestep_sincos(float t, float* out, int dim, cudaStream_t s) {
-    timestep_sincos_k<<<cdiv(dim / 2, 128), 128, 0, s>>>(t, out, dim / 2);
+void timestep_sincos(const float* t_dev, float* out, int dim, cudaStream_t s) {
+    timestep_sincos_k<<<cdiv(dim / 2, 128), 128, 0, s>>>(t_dev, out, dim / 2);
     KERNEL_CHECK();
 }
 
@@ -378,6 +379,14 @@ void eta_noise_losses(const float* eps, int n, int has_cfg, float guidance, cons
 }  // namespace etai
 
 namespace etai {
+__global__ void add_f32_k(float* __restrict__ y, const float* __restrict__ x, long n) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
+void add_f32(float* y, const float* x, long n, cudaStream_t s) {
+    add_f32_k<<<cdiv(n, 256), 256, 0, s>>>(y, x, n);
+    KERNEL_CHECK();
+}
 // y += x (used only where an epilogue fusion is impossible, e.g. PnP feature injection between conv2 and the skip add)
 template <typename T>
 __global__ void add_inplace_k(T* __restrict__ y, const T* __restrict__ x, long nvec) {

@@ -31,22 +31,28 @@ static GnPlan gn_plan(long HW, int C) {
     p.threads = (p.cvecs * p.R + 31) / 32 * 32;  // whole warps; the tail threads only help in the fold
     long rpc = 32;
     rpc = 8;
-    while (cdiv(HW, rpc) > 64) rpc *= 2;  // <= 64 chunks: the apply kernel folds them with two partials per lane
+    while (cdiv(HW, rpc) > 128) rpc *= 2;  // <= 128 chunks per batch row; the last CTA folds them
     if (rpc > HW) rpc = HW;
     p.rows_per_chunk = (int)rpc;
     p.chunks = cdiv(HW, rpc);
     return p;
 }
 
+// workspace layout (offsets independent of the call's batch size, so calls with different B can share one workspace):
+//   [tickets: 64 ints, self-resetting, zero before first use][stats: 64 x 64 float2][partials: B x 256 x G x 2 doubles]
+static constexpr size_t GN_STATS_OFF = 256, GN_PART_OFF = 256 + 64 * 64 * sizeof(float2);
 size_t groupnorm_workspace_bytes(int B, long HW, int C, int groups) {
     (void)HW; (void)C;
-    return (size_t)B * GN_MAX_CHUNKS * groups * 2 * sizeof(double);
+    return GN_PART_OFF + (size_t)B * GN_MAX_CHUNKS * groups * 2 * sizeof(double);
 }
+size_t groupnorm_ticket_offset(int B, int groups) { (void)B; (void)groups; return 0; }
 
 template <typename T>
-__global__ void gn_stats_k(const T* __restrict__ x, double* __restrict__ ws, long HW, int C, int G, int cvecs, int R,
-                           int rows_per_chunk, int chunks) {
+__global__ void gn_stats_k(const T* __restrict__ x, double* __restrict__ ws, float2* __restrict__ stats,
+                           int* __restrict__ tickets, long HW, int C, int G, int cvecs, int R, int rows_per_chunk,
+                           int chunks, float eps) {
     extern __shared__ float sm[];  // [R][C] sums, [R][C] sumsq
+    __shared__ int s_last;
     int b = blockIdx.y, chunk = blockIdx.x;
     int cv = threadIdx.x % cvecs, r = threadIdx.x / cvecs;
     long row0 = (long)chunk * rows_per_chunk;
@@ -99,21 +105,23 @@ __global__ void gn_stats_k(const T* __restrict__ x, double* __restrict__ ws, lon
             w[1] = aa;
         }
     }
-}
-
-template <typename T, bool SILU>
-__global__ void gn_apply_k(const T* __restrict__ x, T* __restrict__ y, const T* __restrict__ gamma,
-                           const T* __restrict__ beta, const double* __restrict__ ws, long HW, int C, int G, int chunks,
-                           float eps, long vecs_per_batch) {
-    __shared__ float s_mean[64], s_rstd[64];
-    int b = blockIdx.y;
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    // The last CTA of this batch row to finish folds all chunk partials (fixed order -> deterministic) into mean/rstd.
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = atomicAdd(&tickets[b], 1);
+        s_last = (t == chunks - 1);
+        if (s_last) tickets[b] = 0;  // self-resetting for the next launch on this stream
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
     for (int g = warp; g < G; g += nwarps) {
         double a = 0.0, aa = 0.0;
         for (int c = lane; c < chunks; c += 32) {
             const double* w = ws + (((long)b * chunks + c) * G + g) * 2;
-            a += w[0];
-            aa += w[1];
+            a += __ldcg(w);
+            aa += __ldcg(w + 1);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -125,37 +133,59 @@ __global__ void gn_apply_k(const T* __restrict__ x, T* __restrict__ y, const T* 
             double mean = a / n;
             double var = aa / n - mean * mean;
             if (var < 0) var = 0;
-            s_mean[g] = (float)mean;
-            s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+            stats[b * G + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
         }
     }
-    __syncthreads();
-    int cvecs = C / 8, cpg = C / G;
-    const T* xb = x + (long)b * HW * C;
-    T* yb = y + (long)b * HW * C;
-    const long stride = (long)gridDim.x * blockDim.x;
-    for (long i0 = blockIdx.x * (long)blockDim.x + threadIdx.x; i0 < vecs_per_batch; i0 += 2 * stride) {
-        float v[2][8];
-        const long i1 = i0 + stride;
-        const bool has1 = i1 < vecs_per_batch;
-        load8<T>(xb + i0 * 8, v[0]);
-        if (has1) load8<T>(xb + i1 * 8, v[1]);
+}
+
+// apply: thread = fixed 8-channel vector (scale/shift folded once into registers), CTA = slab of pixel rows
+template <typename T, bool SILU>
+__global__ void gn_apply_k(const T* __restrict__ x, T* __restrict__ y, const T* __restrict__ gamma,
+                           const T* __restrict__ beta, const float2* __restrict__ stats, long HW, int C, int G, int cvecs,
+                           int R, int rows_per_cta) {
+    const int b = blockIdx.y;
+    const int cv = threadIdx.x % cvecs, r = threadIdx.x / cvecs;
+    if (r >= R) return;
+    const int cpg = C / G, c0 = cv * 8;
+    float sc[8], sh[8];
+    {
+        float ga[8], be[8];
+        load8<T>(gamma + c0, ga);
+        load8<T>(beta + c0, be);
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const long i = u == 0 ? i0 : i1;
-            if (u == 1 && !has1) break;
-            int c0 = (int)(i % cvecs) * 8;
-            float ga[8], be[8];
-            load8<T>(gamma + c0, ga);
-            load8<T>(beta + c0, be);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                int g = (c0 + j) / cpg;
-                float o = (v[u][j] - s_mean[g]) * s_rstd[g] * ga[j] + be[j];
-                v[u][j] = SILU ? silu_f(o) : o;
-            }
-            store8<T>(yb + i * 8, v[u]);
+        for (int j = 0; j < 8; ++j) {
+            float2 st = stats[b * G + (c0 + j) / cpg];  // (mean, rstd)
+            sc[j] = st.y * ga[j];
+            sh[j] = be[j] - st.x * sc[j];
         }
+    }
+    const T* xb = x + (long)b * HW * C + c0;
+    T* yb = y + (long)b * HW * C + c0;
+    const long row0 = (long)blockIdx.x * rows_per_cta;
+    const long row1 = row0 + rows_per_cta < HW ? row0 + rows_per_cta : HW;
+    long row = row0 + r;
+    for (; row + R < row1; row += 2L * R) {  // two independent 16-byte loads in flight
+        float v0[8], v1[8];
+        load8<T>(xb + row * C, v0);
+        load8<T>(xb + (row + R) * C, v1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float o0 = fmaf(v0[j], sc[j], sh[j]), o1 = fmaf(v1[j], sc[j], sh[j]);
+            v0[j] = SILU ? silu_f(o0) : o0;
+            v1[j] = SILU ? silu_f(o1) : o1;
+        }
+        store8<T>(yb + row * C, v0);
+        store8<T>(yb + (row + R) * C, v1);
+    }
+    for (; row < row1; row += R) {
+        float v0[8];
+        load8<T>(xb + row * C, v0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float o0 = fmaf(v0[j], sc[j], sh[j]);
+            v0[j] = SILU ? silu_f(o0) : o0;
+        }
+        store8<T>(yb + row * C, v0);
     }
 }
 
@@ -166,22 +196,25 @@ void groupnorm(const void* x, void* y, const void* gamma, const void* beta, int 
     ETAI_CHECK(ws != nullptr, ETAI_ERR_ARG, "groupnorm: workspace required");
     GnPlan p = gn_plan(HW, C);
     size_t smem = (size_t)2 * p.R * C * sizeof(float);
-    long vecs = HW * C / 8;
-    // apply grid: ~4 CTAs per SM in total (each CTA re-derives mean/rstd from <= 32 chunk partials, then grid-strides)
-    int ablocks = (int)((vecs + 511) / 512);
-    int cap = (148 * 6 + B - 1) / B;
-    if (ablocks > cap) ablocks = cap;
-    if (ablocks < 1) ablocks = 1;
+    // apply grid: about 6 CTAs per SM in total, each a slab of whole pixel rows
+    long want = (HW * B + 148L * 6 - 1) / (148L * 6);
+    int rows_per_cta = (int)((want + p.R - 1) / p.R) * p.R;
+    if (rows_per_cta < 2 * p.R) rows_per_cta = 2 * p.R;
+    int ablocks = cdiv(HW, rows_per_cta);
+    ETAI_CHECK(B <= 64, ETAI_ERR_ARG, "groupnorm: B <= 64");
+    int* tickets = reinterpret_cast<int*>(ws);
+    float2* stats = reinterpret_cast<float2*>(reinterpret_cast<char*>(ws) + GN_STATS_OFF);
+    double* part = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + GN_PART_OFF);
     ETAI_DISPATCH_DTYPE(dtype, T, {
-        gn_stats_k<T><<<dim3(p.chunks, B), p.threads, smem, s>>>((const T*)x, (double*)ws, HW, C, groups, p.cvecs, p.R,
-                                                                 p.rows_per_chunk, p.chunks);
+        gn_stats_k<T><<<dim3(p.chunks, B), p.threads, smem, s>>>((const T*)x, part, stats, tickets, HW, C, groups, p.cvecs,
+                                                                 p.R, p.rows_per_chunk, p.chunks, eps);
         KERNEL_CHECK();
         if (silu)
-            gn_apply_k<T, true><<<dim3(ablocks, B), 256, 0, s>>>((const T*)x, (T*)y, (const T*)gamma, (const T*)beta,
-                                                                 (const double*)ws, HW, C, groups, p.chunks, eps, vecs);
+            gn_apply_k<T, true><<<dim3(ablocks, B), p.threads, 0, s>>>((const T*)x, (T*)y, (const T*)gamma, (const T*)beta,
+                                                                       stats, HW, C, groups, p.cvecs, p.R, rows_per_cta);
         else
-            gn_apply_k<T, false><<<dim3(ablocks, B), 256, 0, s>>>((const T*)x, (T*)y, (const T*)gamma, (const T*)beta,
-                                                                  (const double*)ws, HW, C, groups, p.chunks, eps, vecs);
+            gn_apply_k<T, false><<<dim3(ablocks, B), p.threads, 0, s>>>((const T*)x, (T*)y, (const T*)gamma, (const T*)beta,
+                                                                        stats, HW, C, groups, p.cvecs, p.R, rows_per_cta);
         KERNEL_CHECK();
     });
 }

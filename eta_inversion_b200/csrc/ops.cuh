@@ -36,6 +36,7 @@ void skinny_linear(const float* x, const void* W, const void* bias, float* out, 
 
 // ---------------- normalisation ---------------------------------------------------------------
 size_t groupnorm_workspace_bytes(int B, long HW, int C, int groups);
+size_t groupnorm_ticket_offset(int B, int groups);  // byte offset of the B int tickets (must be zero before first use)
 void groupnorm(const void* x, void* y, const void* gamma, const void* beta, int B, long HW, int C, int groups,
                float eps, bool silu, int dtype, void* ws, cudaStream_t s);
 void layernorm(const void* x, void* y, const void* gamma, const void* beta, long M, int C, float eps, int dtype,
@@ -96,7 +97,8 @@ void upsample2x(const void* in, void* out, int B, int H, int W, int C, int dtype
 void im2col3x3(const void* in, void* out, int B, int H, int W, int C, int stride, int Ho, int Wo, int dtype,
                cudaStream_t s);
 void copy_rows(void* base, long row_elems, int src_row, int n_src, int dst_row, int n_dst, int dtype, cudaStream_t s);
-void timestep_sincos(float t, float* out, int dim, cudaStream_t s);
+void timestep_sincos(const float* t_dev, float* out, int dim, cudaStream_t s);
+void add_f32(float* y, const float* x, long n, cudaStream_t s);
 void add_inplace(void* y, const void* x, long n, int dtype, cudaStream_t s);
 // weight repack: OIHW -> O,(ky,kx),I ; optional GEGLU row interleave
 void pack_conv_weight(const float* oihw, void* out, int O, int I, int Opad, int Ipad, int dtype, cudaStream_t s);

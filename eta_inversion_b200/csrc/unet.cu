@@ -11,6 +11,7 @@
 #include <string>
 #include <cstring>
 #include <cmath>
+#include <cstdlib>
 
 #include "ops.cuh"
 
@@ -80,6 +81,19 @@ struct etai_unet {
     void* gn_ws = nullptr;
     void* tc_ws = nullptr;
     size_t tc_ws_bytes = 0;
+    // ---- CUDA-graph replay: all per-call inputs are staged into engine-owned buffers (stable addresses), the kernel
+    // schedule of one forward is captured once per (batch, control structure) key and replayed afterwards.
+    cudaStream_t gs = nullptr;          // engine stream (capture on the legacy default stream is not allowed)
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    char* in_stage = nullptr;           // latent  [max_batch,4,hw,hw] (io dtype, <= 4 bytes/elem)
+    char* out_stage = nullptr;          // eps out
+    float* t_dev = nullptr;
+    float *c_mapper = nullptr, *c_blend = nullptr, *c_eq = nullptr, *c_alpha = nullptr;  // staged PtP tables
+    float* c_store[3] = {nullptr, nullptr, nullptr};  // per-forward attention-store sums per place
+    bool use_graphs = true;
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; int seen = 0; int64_t launches = 0; };
+    std::unordered_map<std::string, GraphEntry> graphs;
+    int64_t graph_replays = 0;
     void* map16_buf = nullptr;      // prompt-to-prompt mapper in the tcgen05 B-operand form (per forward)
     float* store_part_buf = nullptr;  // per-head attention-store partials
     bool map16_ready = false;
@@ -254,6 +268,7 @@ struct etai_unet {
     void set_context(const void* ctx, int io_dtype, int B, cudaStream_t s);
     void forward(const void* latent, float t, int io_dtype, int B, const etai_attn_ctrl* ctrl, void* eps_out,
                  cudaStream_t s);
+    void run_body(int io_dtype, int B, const etai_attn_ctrl* ctrl, cudaStream_t s);
 
     // ---- op wrappers --------------------------------------------------------------------------
     void gemm(GemmArgs& a, cudaStream_t s) {
@@ -481,9 +496,12 @@ void* etai_unet::transformer(const void* x, int B, int H, int W, const Tfm& t, c
     return linear(h, M, t.pout, x, s);
 }
 
-void etai_unet::set_context(const void* ctx, int io_dtype, int B, cudaStream_t s) {
+void etai_unet::set_context(const void* ctx, int io_dtype, int B, cudaStream_t user) {
     ETAI_CHECK(B >= 1 && B <= cfg.max_batch, ETAI_ERR_ARG, "set_context: batch out of range");
     long M = (long)B * cfg.ctx_len;
+    cudaStream_t s = gs;
+    CUDA_CHECK(cudaEventRecord(ev_in, user));
+    CUDA_CHECK(cudaStreamWaitEvent(gs, ev_in, 0));
     convert(ctx, io_dtype, ctx_buf, dt, M * cfg.cross_dim, s);
     launches += 1;
     GemmArgs a;
@@ -491,15 +509,16 @@ void etai_unet::set_context(const void* ctx, int io_dtype, int B, cudaStream_t s
     a.M = M; a.N = kv_all.n; a.K = kv_all.k; a.lda = kv_all.k; a.ldc = kv_all.n;
     gemm(a, s);
     ctx_rows = B;
+    CUDA_CHECK(cudaEventRecord(ev_out, gs));
+    CUDA_CHECK(cudaStreamWaitEvent(user, ev_out, 0));
 }
 
-void etai_unet::forward(const void* latent, float t, int io_dtype, int B, const etai_attn_ctrl* ctrl, void* eps_out,
-                        cudaStream_t s) {
+// The kernel schedule of one forward.  Inputs/outputs are the engine-owned staging buffers; `ctrl` already points at
+// engine-owned tables, so the same schedule can be captured into a CUDA graph and replayed.
+void etai_unet::run_body(int io_dtype, int B, const etai_attn_ctrl* ctrl, cudaStream_t s) {
     const bool planning = arena.base == nullptr;
-    if (!planning) {
-        ETAI_CHECK(B >= 1 && B <= cfg.max_batch, ETAI_ERR_ARG, "forward: batch out of range");
-        ETAI_CHECK(ctx_rows == B, ETAI_ERR_STATE, "forward: etai_unet_set_context must be called with the same batch first");
-    }
+    const void* latent = in_stage;
+    void* eps_out = out_stage;
     const int* c = cfg.block_out_channels;
     const int temb = c[0] * 4;
     int H = cfg.latent_hw, W = cfg.latent_hw;
@@ -508,13 +527,19 @@ void etai_unet::forward(const void* latent, float t, int io_dtype, int B, const 
     // time embedding (t is shared by all rows): all fp32, M = 1 skinny GEMMs
     if (!planning) {
         cudaEvent_t e = prof_begin(s);
-        timestep_sincos(t, tbuf + TB_SIN, c[0], s);
+        timestep_sincos(t_dev, tbuf + TB_SIN, c[0], s);
         skinny_linear(tbuf + TB_SIN, time1.w, time1.b, tbuf + TB_H1, 1, temb, c[0], 1, dt, s);        // silu(linear_1)
         skinny_linear(tbuf + TB_H1, time2.w, time2.b, tbuf + TB_ST, 1, temb, temb, 1, dt, s);          // silu(temb)
         skinny_linear(tbuf + TB_ST, temb_all.w, temb_all.b, tbuf + TB_PROJ, 1, temb_all.n, temb, 0, dt, s);
         prof_end(ETAI_PROF_OTHER, e, 4, s);
     }
 
+    if (!planning && ctrl && (ctrl->flags & ETAI_CTRL_CROSS_STORE)) {
+        size_t n = (size_t)ctrl->n_store_rows * ctrl->store_res * ctrl->store_res * cfg.ctx_len * sizeof(float);
+        float* acc[3] = {ctrl->store_down, ctrl->store_mid, ctrl->store_up};
+        for (int i = 0; i < 3; ++i)
+            if (acc[i]) CUDA_CHECK(cudaMemsetAsync(acc[i], 0, n, s));
+    }
     map16_ready = false;
     if (!planning && tc && ctrl && (ctrl->flags & ETAI_CTRL_CROSS_EDIT)) {
         cudaEvent_t e = prof_begin(s);
@@ -586,12 +611,110 @@ void etai_unet::forward(const void* latent, float t, int io_dtype, int B, const 
     }
 }
 
+static std::string graph_key(int io_dtype, int B, const etai_attn_ctrl* c) {
+    std::string k;
+    auto put = [&](const void* p, size_t n) { k.append(reinterpret_cast<const char*>(p), n); };
+    put(&io_dtype, 4); put(&B, 4);
+    int flags = c ? c->flags : 0;
+    put(&flags, 4);
+    if (!c) return k;
+    if (flags & ETAI_CTRL_SELF_REMAP) {
+        put(c->self_q_row, 4 * B); put(c->self_k_row, 4 * B); put(c->self_v_row, 4 * B);
+        put(&c->self_layer_mask, 4); put(&c->self_max_tokens, 4);
+    }
+    if (flags & ETAI_CTRL_CROSS_EDIT) {
+        put(&c->n_pairs, 4); put(c->edit_base_row, 4 * c->n_pairs); put(c->edit_tgt_row, 4 * c->n_pairs);
+    }
+    if (flags & ETAI_CTRL_CROSS_STORE) {
+        put(&c->store_res, 4); put(&c->n_store_rows, 4); put(c->store_row, 4 * c->n_store_rows);
+        int places = (c->store_down ? 1 : 0) | (c->store_mid ? 2 : 0) | (c->store_up ? 4 : 0);
+        put(&places, 4);
+    }
+    put(&c->conv_inject_rows, 4);
+    return k;
+}
+
+void etai_unet::forward(const void* latent, float t, int io_dtype, int B, const etai_attn_ctrl* ctrl, void* eps_out,
+                        cudaStream_t user) {
+    ETAI_CHECK(B >= 1 && B <= cfg.max_batch, ETAI_ERR_ARG, "forward: batch out of range");
+    ETAI_CHECK(ctx_rows == B, ETAI_ERR_STATE, "forward: etai_unet_set_context must be called with the same batch first");
+    const int L = cfg.ctx_len;
+    const size_t io_bytes = (size_t)B * 4 * cfg.latent_hw * cfg.latent_hw * dtype_size(io_dtype);
+    // ---- hand over from the caller's stream to the engine stream ----
+    CUDA_CHECK(cudaEventRecord(ev_in, user));
+    CUDA_CHECK(cudaStreamWaitEvent(gs, ev_in, 0));
+    // ---- prologue: stage every per-call input at a stable address ----
+    CUDA_CHECK(cudaMemcpyAsync(in_stage, latent, io_bytes, cudaMemcpyDeviceToDevice, gs));
+    CUDA_CHECK(cudaMemcpyAsync(t_dev, &t, sizeof(float), cudaMemcpyHostToDevice, gs));  // pageable 4-byte copy: staged by the driver
+    etai_attn_ctrl ic;
+    const etai_attn_ctrl* body_ctrl = nullptr;
+    if (ctrl) {
+        ic = *ctrl;
+        if (ctrl->flags & ETAI_CTRL_CROSS_EDIT) {
+            const int P = ctrl->n_pairs;
+            CUDA_CHECK(cudaMemcpyAsync(c_mapper, ctrl->mapper, (size_t)P * L * L * 4, cudaMemcpyDeviceToDevice, gs));
+            CUDA_CHECK(cudaMemcpyAsync(c_blend, ctrl->blend_a, (size_t)P * L * 4, cudaMemcpyDeviceToDevice, gs));
+            CUDA_CHECK(cudaMemcpyAsync(c_eq, ctrl->equalizer, (size_t)P * L * 4, cudaMemcpyDeviceToDevice, gs));
+            CUDA_CHECK(cudaMemcpyAsync(c_alpha, ctrl->alpha_step, (size_t)P * L * 4, cudaMemcpyDeviceToDevice, gs));
+            ic.mapper = c_mapper; ic.blend_a = c_blend; ic.equalizer = c_eq; ic.alpha_step = c_alpha;
+        }
+        if (ctrl->flags & ETAI_CTRL_CROSS_STORE) {
+            ETAI_CHECK(ctrl->store_res <= 32, ETAI_ERR_ARG, "attention store resolution must be <= 32");
+            ic.store_down = ctrl->store_down ? c_store[0] : nullptr;
+            ic.store_mid = ctrl->store_mid ? c_store[1] : nullptr;
+            ic.store_up = ctrl->store_up ? c_store[2] : nullptr;
+        }
+        body_ctrl = &ic;
+    }
+    // ---- the schedule: eager the first time a key is seen, captured the second time, replayed afterwards ----
+    bool done = false;
+    if (use_graphs && !prof_on) {
+        GraphEntry& ge = graphs[graph_key(io_dtype, B, ctrl)];
+        if (ge.exec) {
+            CUDA_CHECK(cudaGraphLaunch(ge.exec, gs));
+            launches += ge.launches;
+            ++graph_replays;
+            done = true;
+        } else if (ge.seen >= 1) {
+            int64_t l0 = launches;
+            cudaGraph_t graph = nullptr;
+            CUDA_CHECK(cudaStreamBeginCapture(gs, cudaStreamCaptureModeRelaxed));
+            try {
+                run_body(io_dtype, B, body_ctrl, gs);
+            } catch (...) {
+                cudaStreamEndCapture(gs, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                throw;
+            }
+            CUDA_CHECK(cudaStreamEndCapture(gs, &graph));
+            ge.launches = launches - l0;
+            CUDA_CHECK(cudaGraphInstantiate(&ge.exec, graph, 0));
+            CUDA_CHECK(cudaGraphDestroy(graph));
+            CUDA_CHECK(cudaGraphLaunch(ge.exec, gs));
+            done = true;
+        } else {
+            ge.seen = 1;
+        }
+    }
+    if (!done) run_body(io_dtype, B, body_ctrl, gs);
+    // ---- epilogue: results back to the caller's buffers ----
+    CUDA_CHECK(cudaMemcpyAsync(eps_out, out_stage, io_bytes, cudaMemcpyDeviceToDevice, gs));
+    if (ctrl && (ctrl->flags & ETAI_CTRL_CROSS_STORE)) {
+        long n = (long)ctrl->n_store_rows * ctrl->store_res * ctrl->store_res * L;
+        float* user_acc[3] = {ctrl->store_down, ctrl->store_mid, ctrl->store_up};
+        for (int i = 0; i < 3; ++i)
+            if (user_acc[i]) { add_f32(user_acc[i], c_store[i], n, gs); launches += 1; }
+    }
+    CUDA_CHECK(cudaEventRecord(ev_out, gs));
+    CUDA_CHECK(cudaStreamWaitEvent(user, ev_out, 0));
+}
+
 void etai_unet::plan_workspace() {
     // dry run with a null arena to size it for max_batch
     arena.base = nullptr;
     arena.cap = 0;
     arena.peak = 0;
-    forward(nullptr, 0.f, ETAI_F32, cfg.max_batch, nullptr, nullptr, 0);
+    run_body(ETAI_F32, cfg.max_batch, nullptr, 0);
     size_t need = arena.peak + 4096;
     void* p = nullptr;
     CUDA_CHECK(cudaMalloc(&p, need));
@@ -603,8 +726,25 @@ void etai_unet::plan_workspace() {
     CUDA_CHECK(cudaMalloc(&kv_cache, (size_t)ctx_m * kv_total * esz));
     CUDA_CHECK(cudaMalloc(&ctx_buf, (size_t)ctx_m * cfg.cross_dim * esz));
     CUDA_CHECK(cudaMalloc((void**)&tbuf, (size_t)(TB_PROJ + temb_total + 64) * sizeof(float)));
+    {
+        size_t io = (size_t)cfg.max_batch * 4 * cfg.latent_hw * cfg.latent_hw * 4;
+        CUDA_CHECK(cudaMalloc((void**)&in_stage, io));
+        CUDA_CHECK(cudaMalloc((void**)&out_stage, io));
+        CUDA_CHECK(cudaMalloc((void**)&t_dev, 256));
+        const int L = cfg.ctx_len;
+        CUDA_CHECK(cudaMalloc((void**)&c_mapper, (size_t)ETAI_MAX_PAIRS * L * L * 4));
+        CUDA_CHECK(cudaMalloc((void**)&c_blend, (size_t)ETAI_MAX_PAIRS * L * 4));
+        CUDA_CHECK(cudaMalloc((void**)&c_eq, (size_t)ETAI_MAX_PAIRS * L * 4));
+        CUDA_CHECK(cudaMalloc((void**)&c_alpha, (size_t)ETAI_MAX_PAIRS * L * 4));
+        for (int i = 0; i < 3; ++i) CUDA_CHECK(cudaMalloc((void**)&c_store[i], (size_t)cfg.max_batch * 1024 * L * 4));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&gs, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+        workspace_bytes += 2 * io + 3 * (size_t)cfg.max_batch * 1024 * L * 4;
+    }
     size_t gws = groupnorm_workspace_bytes(cfg.max_batch, 0, 0, 32);
     CUDA_CHECK(cudaMalloc(&gn_ws, gws));
+    CUDA_CHECK(cudaMemset(gn_ws, 0, gws));  // tickets start at zero and reset themselves
     // im2col scratch for the stride-2 convs on the tcgen05 path: largest is B*32*32 x 9*c0
     tc_ws_bytes = 0;
     if (tc) {
@@ -677,6 +817,7 @@ int etai_unet_create(etai_unet** out, const etai_unet_cfg* cfg, const etai_tenso
         h->dt = cfg->dtype;
         h->esz = dtype_size(cfg->dtype);
         h->tc = cfg->dtype != ETAI_F32 && cfg->math_mode == ETAI_MATH_AUTO;
+        if (const char* e = getenv("ETAI_NO_GRAPHS")) h->use_graphs = !(e[0] == '1');
         h->build(weights, n_weights);
         h->plan_workspace();
     } catch (...) {
@@ -696,6 +837,16 @@ int etai_unet_destroy(etai_unet* h) {
     if (h->ctx_buf) cudaFree(h->ctx_buf);
     if (h->tbuf) cudaFree(h->tbuf);
     if (h->gn_ws) cudaFree(h->gn_ws);
+    for (auto& kv : h->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (h->gs) cudaStreamSynchronize(h->gs);
+    void* extra[] = {h->in_stage, h->out_stage, h->t_dev, h->c_mapper, h->c_blend, h->c_eq, h->c_alpha, h->c_store[0],
+                     h->c_store[1], h->c_store[2]};
+    for (void* p : extra)
+        if (p) cudaFree(p);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
+    if (h->gs) cudaStreamDestroy(h->gs);
     if (h->tc_ws) cudaFree(h->tc_ws);
     if (h->map16_buf) cudaFree(h->map16_buf);
     if (h->store_part_buf) cudaFree(h->store_part_buf);

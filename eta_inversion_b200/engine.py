@@ -240,7 +240,7 @@ def groupnorm(x: torch.Tensor, gamma, beta, groups: int = 32, eps: float = 1e-5,
     _require_cuda(x, "x")
     B, HW, Cc = x.shape
     out = torch.empty_like(x)
-    ws = torch.empty((B * 256 * groups * 2,), dtype=torch.float64, device=x.device)
+    ws = torch.empty((B * 256 * groups * 2 + 4200,), dtype=torch.float64, device=x.device)
     check(_lib.load().etai_groupnorm(ptr(x), ptr(out), ptr(gamma), ptr(beta), B, HW, Cc, groups, eps, int(silu),
                                      dtype_code(x.dtype), ptr(ws), ws.numel() * 8, stream_ptr()))
     return out
