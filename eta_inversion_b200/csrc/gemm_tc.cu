@@ -34,7 +34,7 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 CUtensorMap make_tmap_16bit(const void* base, int dtype, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                            const uint32_t* box) {
+                            const uint32_t* box, bool swizzle128) {
     CUtensorMap m;
     cuuint64_t gdim[5], gstr[5];
     cuuint32_t b[5], estr[5];
@@ -42,7 +42,7 @@ CUtensorMap make_tmap_16bit(const void* base, int dtype, int rank, const uint64_
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
     CUresult r = get_encode_tiled()(&m, dtype == ETAI_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                                     (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, b, estr,
-                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw Error(ETAI_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
     return m;
@@ -81,8 +81,10 @@ struct Smem {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int EPI_BYTES = 4 * 128 * 64;  // 2 epilogue groups x 2 buffers x [128 rows x 32 cols] 16-bit
+    static constexpr int STAGES = (168 * 1024) / STAGE_BYTES > 6 ? 6 : (168 * 1024) / STAGE_BYTES;
+    static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFF = EPI_OFF + EPI_BYTES;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + slack for manual 1024-B alignment
     static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;  // TMEM columns between the two accumulator buffers
     static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
@@ -94,7 +96,8 @@ struct Smem {
 // the main loop of item i+1.
 template <typename T, int BN, bool CONV>
 __global__ void __launch_bounds__(GT_THREADS, 1)
-gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TcParams p) {
+gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ CUtensorMap tmC, const __grid_constant__ TcParams p) {
     using S = Smem<BN>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -110,6 +113,7 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        prefetch_tmap(&tmC);
         for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS); }
         fence_barrier_init();
@@ -185,13 +189,17 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
         }
     } else {
-        // ===== epilogue: warps 2..9.  TMEM lane quarter = warp % 4; the two warps of a quarter alternate 32-col chunks
+        // ===== epilogue: warps 2..9.  TMEM lane quarter = warp % 4; the two 4-warp groups alternate 32-col chunks.
+        // Each group stages its [128 x 32] (GEGLU: [128 x 16]) 16-bit chunk in shared memory and one elected thread writes
+        // it with a TMA store (coalesced 128-B lines, rows/cols beyond M/N clipped by the tensor map).
         const int quarter = warp & 3;
         const int half = (warp - 2) >> 2;
-        T* C = reinterpret_cast<T*>(p.C);
+        const bool elected = quarter == 0 && lane == 0;
         const T* bias = reinterpret_cast<const T*>(p.bias);
         const T* res = reinterpret_cast<const T*>(p.residual);
-        int li = 0;
+        unsigned char* stage_base = smem + S::EPI_OFF + half * (2 * 128 * 64);
+        const int row_in_tile = quarter * 32 + lane;
+        int li = 0, chunk_ctr = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
             const int tile = item % (p.tiles_m * p.tiles_n), split = item / (p.tiles_m * p.tiles_n);
             const int n0 = (tile % p.tiles_n) * BN;
@@ -199,7 +207,7 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int buf = li & 1;
             mbar_wait(&acc_full[buf], (li >> 1) & 1);
             tc_fence_after();
-            const long m = m0 + quarter * 32 + lane;
+            const long m = m0 + row_in_tile;
             const bool row_ok = m < p.M;
             const uint32_t tacc = tmem_base + (uint32_t)buf * S::ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
@@ -207,11 +215,14 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 float v[32];
                 tmem_ld32(tacc + (uint32_t)c0, v);  // warp-collective
                 const int n = n0 + c0;
-                if (!row_ok || n >= p.N) continue;
+                if (n >= p.N) continue;             // uniform across the group
                 if (p.partial) {  // split-K: raw fp32 partial sums, epilogue happens in splitk_reduce_k
-                    float* dst = p.partial + ((long)split * p.M + m) * p.N + n;
+                    if (row_ok) {
+                        float* dst = p.partial + ((long)split * p.M + m) * p.N + n;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        for (int j = 0; j < 32; j += 4)
+                            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
                     continue;
                 }
                 if (bias) {
@@ -230,29 +241,30 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
                     }
                 }
-                if (p.geglu) {
-                    float o[16];
+                if (res && row_ok && !p.geglu) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = v[2 * j] * gelu_f(v[2 * j + 1]);
-                    T* dst = C + m * p.ldc + n / 2;
+                    for (int j = 0; j < 32; j += 8) {
+                        float r8[8];
+                        load8<T>(res + m * p.ldr + n + j, r8);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[j + i] += r8[i];
+                    }
+                }
+                // ---- stage + TMA store ----
+                unsigned char* sbuf = stage_base + (chunk_ctr & 1) * (128 * 64);
+                if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // buffer used 2 chunks ago is free
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                if (p.geglu) {
+                    float o8[8];
+                    T* dst = reinterpret_cast<T*>(sbuf + row_in_tile * 32);
 #pragma unroll
                     for (int j = 0; j < 16; j += 8) {
-                        float o8[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) o8[i] = o[j + i];
+                        for (int i = 0; i < 8; ++i) o8[i] = v[2 * (j + i)] * gelu_f(v[2 * (j + i) + 1]);
                         store8<T>(dst + j, o8);
                     }
                 } else {
-                    if (res) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            float r8[8];
-                            load8<T>(res + m * p.ldr + n + j, r8);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[j + i] += r8[i];
-                        }
-                    }
-                    T* dst = C + m * p.ldc + n;
+                    T* dst = reinterpret_cast<T*>(sbuf + row_in_tile * 64);
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         float o8[8];
@@ -261,11 +273,22 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         store8<T>(dst + j, o8);
                     }
                 }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                if (elected) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                     reinterpret_cast<uint64_t>(&tmC)),
+                                 "r"(smem_u32(sbuf)), "r"(p.geglu ? n / 2 : n), "r"((int)m0)
+                                 : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                ++chunk_ctr;
             }
             tc_fence_before();  // TMEM reads of this accumulator are done
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
+        if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -320,7 +343,7 @@ int num_sms() {
 }
 
 template <typename T, int BN, bool CONV>
-void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, cudaStream_t s) {
+void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TcParams& p, cudaStream_t s) {
     using S = Smem<BN>;
     static bool configured = false;
     if (!configured) {
@@ -329,7 +352,7 @@ void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcParams& p, c
     }
     int items = p.tiles_m * p.tiles_n * p.splits;
     int grid = items < num_sms() ? items : num_sms();
-    gemm_tc_k<T, BN, CONV><<<grid, GT_THREADS, S::TOTAL, s>>>(tmA, tmB, p);
+    gemm_tc_k<T, BN, CONV><<<grid, GT_THREADS, S::TOTAL, s>>>(tmA, tmB, tmC, p);
     KERNEL_CHECK();
     if (p.partial) {
         long total = p.M * p.N / 4;
@@ -405,12 +428,20 @@ void gemm_tc(const GemmArgs& a0, void* ws, size_t ws_bytes, cudaStream_t s) {
         tmA = make_tmap_16bit(a.A, a.dtype, 2, dims, str, box);
         p.num_kb = a.K / BK;
     }
+    CUtensorMap tmC;
+    {
+        const int n_out = a.geglu ? a.N / 2 : a.N;
+        uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)a.M};
+        uint64_t str[1] = {(uint64_t)a.ldc * 2};
+        uint32_t box[2] = {(uint32_t)(a.geglu ? 16 : 32), (uint32_t)BM};
+        tmC = make_tmap_16bit(a.C, a.dtype, 2, dims, str, box, /*swizzle128=*/false);
+    }
     // split-K for the low-resolution layers (few output tiles, K up to 23040): fill the SMs with K slices, fp32
     // partials in the workspace, fixed-order reduction + epilogue in a second launch
     p.splits = 1;
     p.kb_per_split = p.num_kb;
     const int tiles = p.tiles_m * p.tiles_n;
-    if (tiles * 2 <= num_sms() && p.num_kb >= 8 && ws != nullptr) {
+    if (tiles * 2 <= num_sms() && p.num_kb >= 36 && ws != nullptr) {
         int want = num_sms() / tiles;
         if (want > 16) want = 16;
         if (want > p.num_kb / 4) want = p.num_kb / 4;
@@ -425,11 +456,11 @@ void gemm_tc(const GemmArgs& a0, void* ws, size_t ws_bytes, cudaStream_t s) {
 #define LAUNCH(T)                                                            \
     do {                                                                     \
         if (BN == 160) {                                                     \
-            if (a.conv) launch<T, 160, true>(tmA, tmB, p, s);                \
-            else launch<T, 160, false>(tmA, tmB, p, s);                      \
+            if (a.conv) launch<T, 160, true>(tmA, tmB, tmC, p, s);           \
+            else launch<T, 160, false>(tmA, tmB, tmC, p, s);                 \
         } else {                                                             \
-            if (a.conv) launch<T, 128, true>(tmA, tmB, p, s);                \
-            else launch<T, 128, false>(tmA, tmB, p, s);                      \
+            if (a.conv) launch<T, 128, true>(tmA, tmB, tmC, p, s);           \
+            else launch<T, 128, false>(tmA, tmB, tmC, p, s);                 \
         }                                                                    \
     } while (0)
     if (a.dtype == ETAI_F16) LAUNCH(__half);

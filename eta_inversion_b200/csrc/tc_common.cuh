@@ -142,7 +142,7 @@ EncodeTiledFn get_encode_tiled();
 
 // rank-r tensor map over 16-bit elements, innermost dimension contiguous, 128B swizzle, zero OOB fill
 CUtensorMap make_tmap_16bit(const void* base, int dtype, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                            const uint32_t* box);
+                            const uint32_t* box, bool swizzle128 = true);
 
 }  // namespace tc
 }  // namespace etai
