@@ -151,6 +151,8 @@ def main():
     ap.add_argument("--inv-steps", type=int, default=50, dest="inv_steps")
     ap.add_argument("--variant", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cobatch", type=int, default=4,
+                    help="independent edits walked in lock step per step on each GPU (they share every UNet forward)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -166,12 +168,18 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
 
-    pipe, (preproc, postproc) = etai.load_diffusion_model("synthetic-sd15", f"cuda:{local}", variant=args.variant)
-    inverter = etai.load_inverter(type="etainv", model=pipe, scheduler="ddim", num_inference_steps=args.inv_steps,
-                                  guidance_scale_bwd=7.5)
-    editor = etai.load_editor(type="ptp", inverter=inverter)
-    n_img = W + K
-    host_imgs = [syn.synthetic_image(1000 * rank + i).pin_memory() for i in range(n_img)]
+    from eta_inversion_b200.batching import run_lockstep
+    CB = max(1, args.cobatch)
+    pipe, (preproc, postproc) = etai.load_diffusion_model("synthetic-sd15", f"cuda:{local}", variant=args.variant,
+                                                          max_batch=4 * CB)
+
+    def make_editor(p):
+        inv = etai.load_inverter(type="etainv", model=p, scheduler="ddim", num_inference_steps=args.inv_steps,
+                                 guidance_scale_bwd=7.5)
+        return etai.load_editor(type="ptp", inverter=inv)
+    editor = make_editor(pipe)
+    n_img = (W + K) * CB
+    host_imgs = [syn.synthetic_image(100000 * rank + i).pin_memory() for i in range(n_img)]
     dev_imgs = [h.cuda(non_blocking=True) for h in host_imgs]
 
     def barrier():
@@ -179,20 +187,27 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def edit(img):
-        with torch.no_grad():
-            return editor.edit(img, SRC, TGT, cfg={**PTP_CFG}, inv_cfg=INV_CFG)
+    def edit(imgs):
+        """One step = CB independent edits (different images) walked in lock step."""
+        if CB == 1:
+            with torch.no_grad():
+                return [editor.edit(imgs[0], SRC, TGT, cfg={**PTP_CFG}, inv_cfg=INV_CFG)]
+        jobs = [dict(image=im, source_prompt=SRC, target_prompt=TGT, cfg={**PTP_CFG}, inv_cfg=dict(INV_CFG)) for im in imgs]
+        return run_lockstep(pipe, jobs, make_editor)
+
+    def batch(lst, i):
+        return lst[i * CB:(i + 1) * CB]
 
     # ---- (1) device-resident throughput ----------------------------------------------------------
     for i in range(W):
-        edit(dev_imgs[i])
+        edit(batch(dev_imgs, i))
     barrier()
     l0, s0 = pipe.unet.launch_count, E.LAUNCHES[0]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         ev0.record()
         for i in range(K):
-            edit(dev_imgs[W + i])
+            edit(batch(dev_imgs, W + i))
         ev1.record()
         barrier()
     launches = (pipe.unet.launch_count - l0) + (E.LAUNCHES[0] - s0)
@@ -206,22 +221,34 @@ def main():
     t0 = time.perf_counter()
     d2h = 0
     for i in range(K):
-        img = host_imgs[W + i].to(f"cuda:{local}", non_blocking=True)
-        res = edit(img)
-        out = [postproc(res["image"]), postproc(res["image_inv"])]  # device -> host uint8 images (cv2.imwrite input)
-        d2h = res["image"].numel() * res["image"].element_size() * 2
+        imgs = [h.to(f"cuda:{local}", non_blocking=True) for h in batch(host_imgs, W + i)]
+        d2h = 0
+        for res in edit(imgs):
+            out = [postproc(res["image"]), postproc(res["image_inv"])]  # device -> host uint8 images (cv2.imwrite input)
+            d2h += res["image"].numel() * res["image"].element_size() * 2
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
-    h2d = host_imgs[0].numel() * host_imgs[0].element_size()
+    h2d = host_imgs[0].numel() * host_imgs[0].element_size() * CB
+
+    # ---- (2b) share of the step spent inside UNet forwards (graph replay, CUDA events), one more step ----
+    pipe.unet.time_forwards(True)
+    barrier()
+    t0 = time.perf_counter()
+    edit(batch(dev_imgs, W))
+    barrier()
+    step_wall_ms = (time.perf_counter() - t0) * 1e3
+    unet_graph_ms = pipe.unet.time_forwards(False)
 
     # ---- (3) per-category device time of one edit (CUDA events around every op; not part of the timings above) ---
     pipe.unet.profile(True)
-    edit(dev_imgs[W])
+    edit(batch(dev_imgs, W))
     torch.cuda.synchronize()
     prof = pipe.unet.profile(False)
+    for v in prof.values():
+        v["ms"] /= CB  # per edit
 
     if rank != 0:
         if world > 1:
@@ -237,17 +264,19 @@ def main():
     breakdown = {k: {"ms_per_edit": round(v["ms"], 2), "launches": v["launches"],
                      "tflops": round(2.0 * macs[k] * rows / 1e12 / (v["ms"] / 1e3), 1) if k in macs and v["ms"] > 0 else None}
                  for k, v in prof.items()}
-    value = world * K / (ms_total / 1e3)
+    value = world * K * CB / (ms_total / 1e3)
     line = {
         "metric": "edits/sec etainv+PtP SD1.5 512^2 50-step", "value": value, "unit": "edits/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.variant, "data": "synthetic",
         "config": {"workload": workload_name(args.inv_steps), "inv_steps": args.inv_steps, "unet_rows_per_edit": rows,
-                   "ms_per_unet_step_avg": round(unet_ms / (2 * args.inv_steps), 3),
+                   "edits_per_step": CB, "cobatch": f"{CB} independent edits per GPU share each UNet forward (B={2 * CB} inversion, B={4 * CB} edit)",
+                   "ms_per_unet_forward_avg": round(unet_graph_ms / (2 * args.inv_steps), 3),
+                   "unet_share_of_step": round(unet_graph_ms / step_wall_ms, 3),
                    "l2": "no explicit flush: every UNet forward streams 1.72 GB of fp16 weights (>> 126 MB L2)",
                    "parallelism": f"per-image sharding, {world} independent rank(s), no collective in the loop"},
         "clocks": clocks.summary(),
-        "e2e": {"value": world * K / e2e_s, "unit": "edits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": world * K * CB / e2e_s, "unit": "edits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": {"conv3x3": "gemm_tc_k<conv>", "gemm": "gemm_tc_k<dense>",
                                                      "self_attn": "attention"}[dom],

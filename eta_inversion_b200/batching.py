@@ -1,0 +1,177 @@
+"""Lock-step co-batching of independent edits on one GPU.
+
+The reference runs one edit at a time per process (eval.py:65-109), which at B200 speed leaves the UNet forward
+latency-bound: at B=2 / B=4 most of the ~420 kernels of a forward are far too small to fill 148 SMs.  Edits are
+independent, so k of them can walk their loops in lock step and share every UNet forward:
+each edit ("lane") keeps its own unmodified inverter / editor / controller objects and runs in its own Python thread;
+the lanes' ``unet(...)`` calls rendez-vous here, are concatenated along the batch dimension (rows of lane l are
+[l*B, (l+1)*B)), their attention-control descriptors are merged (row indices shifted, PtP tables stacked, one pair per
+lane) and ONE engine forward serves all lanes.  Nothing else is shared: schedulers, noise, LocalBlend and the VAE
+stay per lane, so results equal the sequential ones (bit-exact on the fp32 path, whose kernels are batch-invariant).
+"""
+from __future__ import annotations
+
+import copy
+import threading
+from typing import Any, Callable, Dict, List, Optional, Sequence
+
+import torch
+
+from .engine import AttnControl, UNetEngine, UNetOutput
+
+
+class _LaneUNet:
+    """What lane `lane` sees as ``pipe.unet``."""
+
+    def __init__(self, group: "LockstepGroup", lane: int) -> None:
+        self._group, self._lane = group, lane
+
+    def __getattr__(self, name):  # dtype, device, latent_hw, launch_count, ...
+        return getattr(self._group.engine, name)
+
+    def __call__(self, sample, timestep, encoder_hidden_states=None, control=None, **kwargs) -> UNetOutput:
+        return self._group.forward(self._lane, sample, timestep, encoder_hidden_states, control)
+
+
+class LockstepGroup:
+    def __init__(self, engine: UNetEngine, lanes: int, timeout_s: float = 600.0) -> None:
+        self.engine, self.lanes, self.timeout = engine, lanes, timeout_s
+        self._barrier = threading.Barrier(lanes)
+        self._req: List[Any] = [None] * lanes
+        self._out: List[Any] = [None] * lanes
+        self._err: Optional[BaseException] = None
+        self._ctx_key, self._ctx_cat = None, None
+        self.forwards = 0
+
+    def lane_unet(self, lane: int) -> _LaneUNet:
+        return _LaneUNet(self, lane)
+
+    def abort(self) -> None:
+        self._barrier.abort()
+
+    # ---- called concurrently by the lane threads ---------------------------------------------------
+    def forward(self, lane: int, sample, timestep, ctx, control) -> UNetOutput:
+        self._req[lane] = (sample, timestep, ctx, control)
+        try:
+            if self._barrier.wait(self.timeout) == 0:  # every lane has posted its request; one thread runs the engine
+                try:
+                    self._run()
+                except BaseException as e:  # noqa: BLE001 - re-raised in every lane below
+                    self._err = e
+            self._barrier.wait(self.timeout)
+        except threading.BrokenBarrierError:
+            raise RuntimeError("etai lockstep: a lane left the loop early (edits in one group must take the same "
+                               "number of UNet forwards)") from self._err
+        if self._err is not None:
+            raise RuntimeError(f"etai lockstep: batched forward failed: {self._err}") from self._err
+        return UNetOutput(self._out[lane])
+
+    # ---- leader ------------------------------------------------------------------------------------
+    def _run(self) -> None:
+        reqs = self._req
+        B = reqs[0][0].shape[0]
+        t0 = float(reqs[0][1])
+        for s, t, c, _ in reqs:
+            if s.shape[0] != B or float(t) != t0 or c is None or c.shape[0] != B:
+                raise RuntimeError("lanes disagree on batch rows / timestep / context rows")
+        sample = torch.cat([r[0] for r in reqs])
+        key = tuple((r[2].data_ptr(), r[2]._version) for r in reqs)
+        if key != self._ctx_key:  # contexts are constant over a loop: concatenate (and re-project K/V) only on change
+            self._ctx_key, self._ctx_cat = key, torch.cat([r[2] for r in reqs]).contiguous()
+        ctrl, scatter = self._merge([r[3] for r in reqs], B)
+        eps = self.engine(sample, t0, encoder_hidden_states=self._ctx_cat, control=ctrl)["sample"]
+        for fn in scatter:
+            fn()
+        for l in range(self.lanes):
+            self._out[l] = eps[l * B:(l + 1) * B]
+        self.forwards += 1
+
+    def _merge(self, ctrls: Sequence[Optional[AttnControl]], B: int):
+        if all(c is None for c in ctrls):
+            return None, []
+        out = AttnControl()
+        scatter: List[Callable[[], None]] = []
+        # self-attention remap: lanes without one keep identity rows
+        if any(c is not None and c.self_rows is not None for c in ctrls):
+            q, k, v = [], [], []
+            masks = {(c.self_layer_mask, c.self_max_tokens) for c in ctrls if c is not None and c.self_rows is not None}
+            if len(masks) != 1:
+                raise RuntimeError("lanes disagree on the self-attention remap window")
+            out.self_layer_mask, out.self_max_tokens = masks.pop()
+            for l, c in enumerate(ctrls):
+                rows = c.self_rows if (c is not None and c.self_rows is not None) else ([*range(B)],) * 3
+                q += [l * B + r for r in rows[0]]
+                k += [l * B + r for r in rows[1]]
+                v += [l * B + r for r in rows[2]]
+            out.self_rows = (q, k, v)
+        # cross-attention edit: one (base, target) pair per lane that edits at this step
+        ed = [(l, c) for l, c in enumerate(ctrls) if c is not None and c.edit_pairs is not None]
+        if ed:
+            out.edit_pairs = [(l * B + b, l * B + t) for l, c in ed for (b, t) in c.edit_pairs]
+            for name in ("mapper", "blend_a", "equalizer", "alpha_step"):
+                setattr(out, name, torch.cat([getattr(c, name) for _, c in ed]).contiguous())
+        # attention store: one combined accumulator per place, scattered back to the lanes' own tensors afterwards
+        st = [(l, c) for l, c in enumerate(ctrls) if c is not None and c.store_rows is not None]
+        if st:
+            res = {c.store_res for _, c in st}
+            if len(res) != 1:
+                raise RuntimeError("lanes disagree on the attention-store resolution")
+            out.store_res = res.pop()
+            out.store_rows = [l * B + r for l, c in st for r in c.store_rows]
+            n = len(out.store_rows)
+            for place in ("store_down", "store_mid", "store_up"):
+                if any(getattr(c, place) is not None for _, c in st):
+                    acc = torch.zeros((n, out.store_res ** 2, 77), dtype=torch.float32, device=self.engine.device)
+                    setattr(out, place, acc)
+                    off = 0
+                    for _, c in st:
+                        m = len(c.store_rows)
+                        dst = getattr(c, place)
+                        if dst is not None:
+                            scatter.append(lambda dst=dst, acc=acc, off=off, m=m: dst.add_(acc[off:off + m]))
+                        off += m
+        if any(c is not None and c.conv_inject_rows for c in ctrls):
+            raise NotImplementedError("Plug-and-Play feature injection is not supported in lock-step groups")
+        return out, scatter
+
+
+def run_lockstep(pipe, jobs: Sequence[Dict[str, Any]], make_editor: Callable[[Any], Any]) -> List[Any]:
+    """Run ``len(jobs)`` edits in lock step on ``pipe``.
+
+    jobs[i]: kwargs of ``Editor.edit`` (image, source_prompt, target_prompt, cfg, inv_cfg).
+    make_editor(lane_pipe) -> editor: builds the lane's own inverter + editor on a per-lane view of the pipeline
+    (same VAE / text encoder / tokenizer, its own scheduler slot and the lock-step UNet proxy).
+    The engine behind ``pipe.unet`` must have been created with ``max_batch >= 4 * len(jobs)``.
+    """
+    k = len(jobs)
+    group = LockstepGroup(pipe.unet, k)
+    editors = []
+    for l in range(k):
+        lane_pipe = copy.copy(pipe)
+        lane_pipe.unet = group.lane_unet(l)
+        editors.append(make_editor(lane_pipe))
+    results: List[Any] = [None] * k
+    errors: List[Optional[BaseException]] = [None] * k
+    dev = pipe.device
+
+    def work(l: int) -> None:
+        try:
+            torch.cuda.set_device(dev)
+            with torch.no_grad():
+                results[l] = editors[l].edit(**jobs[l])
+        except BaseException as e:  # noqa: BLE001
+            errors[l] = e
+            group.abort()
+
+    threads = [threading.Thread(target=work, args=(l,), name=f"etai-lane-{l}") for l in range(k)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for e in errors:
+        if e is not None and not isinstance(e, threading.BrokenBarrierError):
+            raise e
+    for e in errors:
+        if e is not None:
+            raise e
+    return results

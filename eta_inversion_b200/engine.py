@@ -144,6 +144,7 @@ class UNetEngine:
         self._h = h
         self._lib = lib
         self._ctx_key = None
+        self._timing = None  # list of (start, end) torch events when forward timing is switched on
 
     def close(self):
         if getattr(self, "_h", None):
@@ -172,6 +173,16 @@ class UNetEngine:
         check(self._lib.etai_unet_profile(self._h, int(enable), ms, cnt))
         return {n: {"ms": float(ms[i]), "launches": int(cnt[i])} for i, n in enumerate(self.PROF_CATEGORIES)}
 
+    def time_forwards(self, enable: bool) -> float:
+        """Device time (ms) spent in forward() calls since timing was switched on (CUDA events on the caller's stream,
+        works with graph replay); then switch timing on/off."""
+        ms = 0.0
+        if self._timing:
+            torch.cuda.synchronize(self.device)
+            ms = sum(a.elapsed_time(b) for a, b in self._timing)
+        self._timing = [] if enable else None
+        return ms
+
     def set_context(self, ctx: torch.Tensor) -> None:
         _require_cuda(ctx, "encoder_hidden_states")
         if ctx.ndim != 3 or ctx.shape[1] != self.ctx_len or ctx.shape[2] != self.cross_dim:
@@ -196,8 +207,14 @@ class UNetEngine:
         out = torch.empty_like(sample)
         cs = ctrl.to_struct() if ctrl is not None else None
         with torch.cuda.device(self.device):
+            if self._timing is not None:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             check(self._lib.etai_unet_forward(self._h, ptr(sample), t, dtype_code(sample.dtype), B,
                                               C.byref(cs) if cs is not None else None, ptr(out), stream_ptr()))
+            if self._timing is not None:
+                ev[1].record()
+                self._timing.append(ev)
         return UNetOutput(out)
 
     __call__ = forward

@@ -114,6 +114,15 @@ class DiffusionInversion:
         return (latent * 0.18215).float()  # latent trajectory is kept in fp32
 
     def _embed(self, text: str) -> torch.Tensor:
+        cache = self.model.__dict__.setdefault("_text_embedding_cache", {})  # weights are frozen: same text, same embedding
+        if text in cache:
+            return cache[text]
+        emb = self._embed_uncached(text)
+        if len(cache) < 256:
+            cache[text] = emb
+        return emb
+
+    def _embed_uncached(self, text: str) -> torch.Tensor:
         tok = self.model.tokenizer([text], padding="max_length", max_length=self.model.tokenizer.model_max_length,
                                    truncation=True, return_tensors="pt")
         return self.model.text_encoder(tok.input_ids.to(self.model.device))[0].float()

@@ -139,7 +139,7 @@ def load_diffusion_model(model: str = "synthetic-sd15", device: str = "cuda", pr
     vae = AutoencoderKL().eval().requires_grad_(False)
     vae.load_state_dict(vae_state_dict if vae_state_dict is not None
                         else synthetic.random_state_dict(synthetic.vae_param_spec(), seed + 1), strict=True)
-    vae = vae.to(dev, dtype)
-    text_encoder = make_text_encoder(seed).to(dev)
+    vae = vae.to(dev, dtype).to(memory_format=torch.channels_last)
+    text_encoder = make_text_encoder(seed).to(dev, dtype)  # 16-bit variants run CLIP in 16-bit as the reference does
     pipe = EtaiPipeline(unet, vae, text_encoder, SyntheticTokenizer(), sd_scheduler(), dev)
     return pipe, (StablePreprocess(str(dev), size=512, **(preproc_args or {})), StablePostProc())

@@ -12,8 +12,23 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+class _GN(nn.GroupNorm):
+    """GroupNorm(+SiLU).  On CUDA it runs the engine's fused NHWC kernel (etai_groupnorm) on the channels_last
+    storage of the activation, which also keeps cuDNN's convolutions in NHWC; on CPU it is plain torch."""
+
+    def forward(self, x, silu: bool = False):
+        if x.is_cuda and x.ndim == 4 and x.shape[1] % 8 == 0:
+            from . import engine as E
+            b, c, h, w = x.shape
+            xh = x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1).reshape(b, h * w, c)
+            y = E.groupnorm(xh, self.weight, self.bias, self.num_groups, self.eps, silu)
+            return y.reshape(b, h, w, c).permute(0, 3, 1, 2)
+        y = super().forward(x)
+        return F.silu(y) if silu else y
+
+
 def _gn(c):
-    return nn.GroupNorm(32, c, eps=1e-6)
+    return _GN(32, c, eps=1e-6)
 
 
 class _Res(nn.Module):
@@ -24,8 +39,8 @@ class _Res(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x):
-        h = self.conv1(F.silu(self.norm1(x)))
-        h = self.conv2(F.silu(self.norm2(h)))
+        h = self.conv1(self.norm1(x, silu=True))
+        h = self.conv2(self.norm2(h, silu=True))
         return (x if self.conv_shortcut is None else self.conv_shortcut(x)) + h
 
 
@@ -38,7 +53,7 @@ class _Attn(nn.Module):
 
     def forward(self, x):
         b, c, h, w = x.shape
-        t = self.group_norm(x).reshape(b, c, h * w).transpose(1, 2)
+        t = self.group_norm(x).reshape(b, c, h * w).transpose(1, 2)  # [B, HW, C]
         o = F.scaled_dot_product_attention(self.to_q(t)[:, None], self.to_k(t)[:, None], self.to_v(t)[:, None])[:, 0]
         return x + self.to_out[0](o).transpose(1, 2).reshape(b, c, h, w)
 
@@ -90,7 +105,7 @@ class _Encoder(nn.Module):
         x = self.conv_in(x)
         for b in self.down_blocks:
             x = b(x)
-        return self.conv_out(F.silu(self.conv_norm_out(self.mid_block(x))))
+        return self.conv_out(self.conv_norm_out(self.mid_block(x), silu=True))
 
 
 class _Decoder(nn.Module):
@@ -106,7 +121,7 @@ class _Decoder(nn.Module):
         x = self.mid_block(self.conv_in(z))
         for b in self.up_blocks:
             x = b(x)
-        return self.conv_out(F.silu(self.conv_norm_out(x)))
+        return self.conv_out(self.conv_norm_out(x, silu=True))
 
 
 class AutoencoderKL(nn.Module):

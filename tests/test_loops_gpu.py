@@ -97,3 +97,30 @@ def test_fp16_psnr_gate(pipe_fp32):
     print(f"fp16 vs fp32 PSNR: edit {p_edit:.2f} dB, reconstruction {p_inv:.2f} dB; pooled max-abs vs reference "
           f"{(pooled - torch.from_numpy(gold['image_pool8'])).abs().max():.3e}")
     assert p_edit >= 35.0 and p_inv >= 35.0
+
+
+def test_lockstep_cobatch_equals_sequential(pipe_fp32):
+    """Two independent edits sharing every UNet forward (B=4 inversion, B=8 edit) reproduce the sequential results:
+    the fp32 kernels are batch-invariant, so the comparison is tight."""
+    import eta_inversion_b200 as etai
+    from eta_inversion_b200 import synthetic as syn
+    from eta_inversion_b200.batching import run_lockstep
+    pipe, _ = etai.load_diffusion_model("synthetic-sd15", "cuda", variant="fp32", max_batch=8)
+    cfg = SCENARIOS["etainv_ptp_replace_5"][3]
+
+    def make_editor(p):
+        inv = etai.load_inverter(type="etainv", model=p, scheduler="ddim", num_inference_steps=4)
+        return etai.load_editor(type="ptp", inverter=inv)
+    jobs = [dict(image=syn.synthetic_image(0).cuda(), source_prompt=SRC, target_prompt=TGT, cfg={**cfg},
+                 inv_cfg=dict(edit_word_idx=(1, 1))),
+            dict(image=syn.synthetic_image(5).cuda(), source_prompt="a dog on a bench", target_prompt="a fox on a bench",
+                 cfg={**cfg, "blend_words": [["dog"], ["fox"]], "equilizer_params": {"words": ["fox"], "values": [2]}},
+                 inv_cfg=dict(edit_word_idx=(1, 1)))]
+    with torch.no_grad():
+        seq = [make_editor(pipe).edit(**{**j, "cfg": {**j["cfg"]}}) for j in jobs]
+    par = run_lockstep(pipe, [{**j, "cfg": {**j["cfg"]}} for j in jobs], make_editor)
+    for a, b in zip(seq, par):
+        err = (a["latent"] - b["latent"]).abs().max().item()
+        print(f"lockstep vs sequential latent max-abs {err:.2e}")
+        assert err < 1e-5
+        assert (a["latent_inv"] - b["latent_inv"]).abs().max().item() < 1e-5
