@@ -1,0 +1,133 @@
+"""CPU tests of the host-side logic (no GPU, no CUDA calls): token alignment / alpha tables / eta schedule against
+goldens produced by the reference's own functions (oracle/make_host_goldens.py), scheduler constants against the
+oracle, the PSNR known answer of the reference's metric test, sharding, and the analytic FLOP count."""
+import json
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+H = json.loads((GOLDEN / "host_logic.json").read_text())
+
+
+@pytest.fixture(scope="module")
+def tok():
+    from eta_inversion_b200.models import SyntheticTokenizer
+    return SyntheticTokenizer()
+
+
+def test_tokenizer_matches_oracle_tokenizer(tok):
+    from oracle.sd15 import SyntheticTokenizer as OracleTok
+    o = OracleTok()
+    for s, t in H["pairs"]:
+        for text in (s, t, ""):
+            assert tok.encode(text) == o.encode(text)
+            assert torch.equal(tok([text]).input_ids, o([text]).input_ids)
+    assert tok("a b").input_ids.shape == (1, 77)
+
+
+def test_refinement_and_replacement_mappers_match_reference(tok):
+    from eta_inversion_b200.utils import seq_aligner
+    for (s, t), ref, rep in zip(H["pairs"], H["refine"], H["replace"]):
+        m, a = seq_aligner.get_refinement_mapper([s, t], tok)
+        assert m[0].tolist() == ref["mapper"] and a[0].tolist() == ref["alphas"]
+        if rep is not None:
+            assert seq_aligner.get_replacement_mapper([s, t], tok)[0].tolist() == rep
+        else:
+            with pytest.raises(ValueError):
+                seq_aligner.get_replacement_mapper([s, t], tok)
+
+
+def test_word_inds_and_alpha_tables_match_reference(tok):
+    from eta_inversion_b200.utils import ptp_utils
+    k = 0
+    for i, (s, t) in enumerate(H["pairs"]):
+        assert [ptp_utils.get_word_inds(t, w, tok).tolist() for w in t.split(" ")] == H["word_inds"][i]
+        for _ in range(2):
+            g = H["alpha"][k]
+            crs = g["crs"] if not isinstance(g["crs"], dict) else {kk: tuple(v) if isinstance(v, list) else v for kk, v in g["crs"].items()}
+            al = ptp_utils.get_time_words_attention_alpha([s, t], 50, crs, tok)
+            assert list(al.shape) == g["shape"] and al.reshape(51, -1).sum(1).tolist() == g["sum_per_step"]
+            k += 1
+
+
+def test_eta_schedule_matches_reference():
+    from eta_inversion_b200.inversion.eta_inversion import make_eta_schedule
+    for name, g in H["eta"].items():
+        spec = g["spec"]
+        spec = tuple(tuple(x) if isinstance(x, list) else x for x in spec) if isinstance(spec, list) else spec
+        v = make_eta_schedule(spec)
+        assert v.shape == (1000,)
+        np.testing.assert_allclose(v[::37], np.array(g["values_every_37"]), rtol=1e-12, atol=1e-15)
+
+
+def test_scheduler_constants_match_oracle():
+    """Host half of the schedulers (alphas, timesteps, variance) vs the oracle restatement of diffusers' DDIMScheduler."""
+    from eta_inversion_b200.models import sd_scheduler
+    from eta_inversion_b200.inverse_schedulers import DDIMInverseScheduler, DDIMScheduler
+    from oracle import sd15
+    ours, ref = sd_scheduler(), sd15.sd_scheduler()
+    assert torch.equal(ours.alphas_cumprod, ref.alphas_cumprod) and ours.config == ref.config
+    for n in (50, 10, 4):
+        a = DDIMScheduler.from_config({**ours.config, "clip_sample": False, "set_alpha_to_one": False})
+        b = sd15.DDIMScheduler.from_config({**ref.config, "clip_sample": False, "set_alpha_to_one": False})
+        a.set_timesteps(n), b.set_timesteps(n)
+        assert torch.equal(a.timesteps, b.timesteps) and a.timesteps[-1] == 1
+        inv = DDIMInverseScheduler.from_scheduler(a)
+        inv.set_timesteps(n)
+        assert inv.timesteps[0] == 1 and inv.timesteps[0] < inv.timesteps[1]
+        for t in a.timesteps.tolist():
+            p = a.prev_timestep(t)
+            assert math.isclose(float(a._get_variance(t, p)), float(b._get_variance(t, p)), rel_tol=0, abs_tol=0)
+            assert a.alpha(p) == float(b.alphas_cumprod[p] if p >= 0 else b.final_alpha_cumprod)
+
+
+def test_psnr_known_answer_of_the_reference_metric_test():
+    """test/test_metrics.py:61-62 of the reference: mse 0.011490068398416042, psnr 19.396774291992188 on its two PNGs."""
+    import cv2
+    from eta_inversion_b200.metrics import psnr
+    from eta_inversion_b200.models import StablePreprocess
+    pre = StablePreprocess("cpu", size=512)
+    a = pre(GOLDEN / "ref_images" / "gnochi_mirror_sq.png")
+    b = pre(GOLDEN / "ref_images" / "gnochi_mirror_sq_edit_example.png")
+    assert a.shape == (1, 3, 512, 512) and -1 <= float(a.min()) and float(a.max()) <= 1
+    assert abs(psnr(b, a) - 19.396774291992188) < 1e-4
+    mse = torch.mean(((a + 1) / 2 - (b + 1) / 2) ** 2).item()
+    assert abs(mse - 0.011490068398416042) < 1e-8
+
+
+def test_flop_count_matches_survey():
+    from eta_inversion_b200 import flops
+    m = flops.unet_macs_per_row()
+    assert abs(m["total"] / 1e9 - 401.637) < 0.01
+    assert abs(m["conv3x3"] / m["total"] - 0.498) < 0.01
+
+
+def test_param_spec_matches_oracle_module_tree():
+    """The product's parameter spec (the loader contract for real diffusers checkpoints) names exactly the tensors of
+    the oracle's UNet / VAE module trees."""
+    from eta_inversion_b200 import synthetic as syn
+    from oracle import sd15
+    with torch.device("meta"):
+        u, v = sd15.UNet2DConditionModel(), sd15.AutoencoderKL()
+    assert {k: tuple(t.shape) for k, t in u.state_dict().items()} == dict(syn.unet_param_spec())
+    assert {k: tuple(t.shape) for k, t in v.state_dict().items()} == dict(syn.vae_param_spec())
+    assert sum(math.prod(s) for _, s in syn.unet_param_spec()) == 859_520_964
+
+
+def test_sharding_covers_every_sample_once():
+    from eta_inversion_b200.sweep import gather_results, group_indices, shard_indices
+    for n, w in ((700, 8), (700, 4), (700, 2), (7, 8), (0, 2), (1, 1)):
+        owned = [shard_indices(n, r, w) for r in range(w)]
+        flat = sorted(i for o in owned for i in o)
+        assert flat == list(range(n))
+        assert max(len(o) for o in owned) - min(len(o) for o in owned) <= 1
+    assert group_indices([0, 8, 16, 24, 32], 2) == [[0, 8], [16, 24], [32]]
+    assert gather_results({0: "a", 1: "b"}, 2, 1) == ["a", "b"]
+    with pytest.raises(RuntimeError):
+        gather_results({0: "a"}, 2, 1)
+    with pytest.raises(ValueError):
+        shard_indices(4, 2, 2)
