@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Sweep driver (BASELINE config 4): edits a set of (image, source prompt, target prompt) samples and writes one PNG
+per sample, sharded PER IMAGE across the GPUs of one box.
+
+    python eval.py --cfg cfg/eval/synthetic_pie.yaml                       # one GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 eval.py --cfg ...
+
+Compared with the reference's eval.py (:27-183): the YAML grid keys (data / model / method / edit_method / edit_cfg)
+and the result layout result/<cfg>/<nn_combo>/imgs/*.png are kept, finished PNGs are skipped unless --override
+(eval_utils.py:260-263); the unit of parallelism is the sample (rank = index mod world, lock-step groups of --cobatch
+inside a rank) instead of one process per config combination, and only per-sample records are gathered at the end.
+The only dataset on this box is the synthetic PIE-shaped one (`data: [{type: synthetic_pie, n: 700}]`)."""
+from __future__ import annotations
+
+import argparse
+import itertools
+import os
+from pathlib import Path
+
+import torch
+import yaml
+
+import eta_inversion_b200 as etai
+from eta_inversion_b200 import synthetic as syn
+from eta_inversion_b200.batching import run_lockstep
+from eta_inversion_b200.sweep import run_sweep
+
+PIE_DEFAULT_PTP = dict(is_replace_controller=False, cross_replace_steps={"default_": .4}, self_replace_steps=0.6)  # pie_bench_data.py:59-70
+WORDS = ["cat", "tiger", "dog", "fox", "house", "castle", "car", "boat", "tree", "tower"]
+
+
+def synthetic_pie_sample(i: int):
+    """PIE-Bench-shaped record (keys of dataset/pie_bench_data.py:113-158) for sample i."""
+    a, b = WORDS[i % len(WORDS)], WORDS[(i + 1 + i // len(WORDS)) % len(WORDS)]
+    if a == b:
+        b = WORDS[(WORDS.index(a) + 3) % len(WORDS)]
+    src, tgt = f"a {a} sitting next to a mirror", f"a {b} sitting next to a mirror"
+    cfg = {**PIE_DEFAULT_PTP, "prompts": [src, tgt], "blend_words": ((a,), (b,)), "equilizer_params": {"words": (b,), "values": (2,)}}
+    return dict(name=f"{i:06d}", image=syn.synthetic_image(i), source_prompt=src, target_prompt=tgt, edit_cfg=cfg,
+                edit_word_idx=(1, 1))
+
+
+def combos(cfg):
+    keys = ("model", "data", "method", "edit_method")
+    for i, vals in enumerate(itertools.product(*[cfg[k] for k in keys])):
+        yield i, dict(zip(keys, vals))
+
+
+def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int) -> None:
+    import cv2
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    spec = yaml.safe_load(Path(cfg).read_text())
+    root = Path("result") / Path(cfg).stem
+    pipe, (_, postproc) = etai.load_diffusion_model("synthetic-sd15", f"cuda:{local}", variant=prec, max_batch=4 * cobatch)
+    for ci, combo in combos(spec):
+        data = combo["data"] if isinstance(combo["data"], dict) else {"type": combo["data"]}
+        n = min(int(data.get("n", 700)), limit) if limit else int(data.get("n", 700))
+        out_dir = root / f"{ci:02d}_{combo['method']['type']}_{combo['edit_method']['type']}" / "imgs"
+        out_dir.mkdir(parents=True, exist_ok=True)
+        method, edit_method = dict(combo["method"]), dict(combo["edit_method"])
+
+        def make_editor(p):
+            inv = etai.load_inverter(model=p, **method)
+            return etai.load_editor(inverter=inv, **edit_method)
+
+        def run_group(idx):
+            samples = [synthetic_pie_sample(i) for i in idx]
+            todo = [s for s in samples if override or not (out_dir / f"{s['name']}.png").exists()]
+            jobs = [dict(image=s["image"].cuda(), source_prompt=s["source_prompt"], target_prompt=s["target_prompt"],
+                         cfg={**s["edit_cfg"]} if edit_method["type"] == "ptp" else None,
+                         inv_cfg=dict(edit_word_idx=s["edit_word_idx"])) for s in todo]
+            results = run_lockstep(pipe, jobs, make_editor) if jobs else []
+            recs = {}
+            for s, r in zip(todo, results):
+                if r is None:
+                    recs[s["name"]] = {"name": s["name"], "status": "unsupported"}
+                    continue
+                cv2.imwrite(str(out_dir / f"{s['name']}.png"), cv2.cvtColor(postproc(r["image"]), cv2.COLOR_RGB2BGR))
+                recs[s["name"]] = {"name": s["name"], "status": "done", "latent_mean": float(r["latent"].mean())}
+            return [recs.get(s["name"], {"name": s["name"], "status": "skipped"}) for s in samples]
+        records = run_sweep(n, rank, world, cobatch, run_group)
+        if rank == 0:
+            (out_dir.parent / "records.yaml").write_text(yaml.safe_dump(records))
+            print(f"combo {ci}: {sum(r['status'] == 'done' for r in records)} edited, "
+                  f"{sum(r['status'] == 'skipped' for r in records)} skipped -> {out_dir}")
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser(description="Run an editing sweep sharded per image across the visible GPUs.")
+    ap.add_argument("--cfg", required=True, help="Config file for evaluation.")
+    ap.add_argument("--cobatch", type=int, default=4, help="Edits walked in lock step per GPU.")
+    ap.add_argument("--override", action="store_true", help="Override old results.")
+    ap.add_argument("--prec", default="fp16", choices=["fp16", "bf16", "fp32"])
+    ap.add_argument("--limit", type=int, default=0, help="Only the first N samples (smoke runs).")
+    main(**vars(ap.parse_args()))
