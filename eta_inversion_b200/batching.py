@@ -75,9 +75,11 @@ class LockstepGroup:
             if s.shape[0] != B or float(t) != t0 or c is None or c.shape[0] != B:
                 raise RuntimeError("lanes disagree on batch rows / timestep / context rows")
         sample = torch.cat([r[0] for r in reqs])
-        key = tuple((r[2].data_ptr(), r[2]._version) for r in reqs)
-        if key != self._ctx_key:  # contexts are constant over a loop: concatenate (and re-project K/V) only on change
-            self._ctx_key, self._ctx_cat = key, torch.cat([r[2] for r in reqs]).contiguous()
+        old = self._ctx_key  # strong references to the lanes' context tensors + their versions (addresses can be reused)
+        same = old is not None and all(o[0] is r[2] and o[1] == r[2]._version for o, r in zip(old, reqs))
+        if not same:  # contexts are constant over a loop: concatenate (and re-project K/V) only on change
+            self._ctx_key = [(r[2], r[2]._version) for r in reqs]
+            self._ctx_cat = torch.cat([r[2] for r in reqs]).contiguous()
         ctrl, scatter = self._merge([r[3] for r in reqs], B)
         eps = self.engine(sample, t0, encoder_hidden_states=self._ctx_cat, control=ctrl)["sample"]
         for fn in scatter:
@@ -164,10 +166,16 @@ def run_lockstep(pipe, jobs: Sequence[Dict[str, Any]], make_editor: Callable[[An
             group.abort()
 
     threads = [threading.Thread(target=work, args=(l,), name=f"etai-lane-{l}") for l in range(k)]
-    for th in threads:
-        th.start()
-    for th in threads:
-        th.join()
+    import sys
+    old_interval = sys.getswitchinterval()
+    sys.setswitchinterval(2e-4)  # lanes hand the GIL over at every rendez-vous; the 5 ms default stalls the others
+    try:
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+    finally:
+        sys.setswitchinterval(old_interval)
     for e in errors:
         if e is not None and not isinstance(e, threading.BrokenBarrierError):
             raise e

@@ -318,8 +318,10 @@ attn_tc2_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     constexpr int KV_OFF = 2 * OP_BYTES;                      // after Q0, Q1
     constexpr int P_OFF = KV_OFF + STAGES * KV_BYTES;         // P0, P1: 2 atoms each
     constexpr int BAR_OFF = P_OFF + 4 * ATOM_BYTES;
-    constexpr int DPAD = ATOMS == 1 ? 48 : 80;
     constexpr int D = ATOMS == 1 ? 40 : 80;
+    // UMMA N of the PV product: d plus one extra column that the softmax threads set to 1.0 in the V tile, so the tensor
+    // core also produces the softmax row sums (fp32, from exactly the 16-bit P it multiplies) in O[:, D]
+    constexpr int DPAD = ATOMS == 1 ? 48 : 96;
     constexpr int O_STRIDE = ATOMS == 1 ? 64 : 96;            // TMEM columns between O0 and O1 (at column 256)
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -433,7 +435,7 @@ attn_tc2_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         float o_acc[DPAD];
 #pragma unroll
         for (int i = 0; i < DPAD; ++i) o_acc[i] = 0.f;
-        float m_run = -INFINITY, l_run = 0.f, alpha_pending = 1.f;
+        float m_run = -INFINITY, alpha_pending = 1.f;
 
         auto fold_o = [&](int j) {
             mbar_wait(&o_full[g], j & 1);
@@ -446,7 +448,7 @@ attn_tc2_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
 #pragma unroll
                 for (int i = 0; i < 32; ++i) o_acc[b * 32 + i] = fmaf(o_acc[b * 32 + i], alpha_pending, v[i]);
             }
-            {
+            if constexpr (DPAD % 32 != 0) {
                 uint32_t rr[16];
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -492,7 +494,8 @@ attn_tc2_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
             const float mb = m_new * p.scale_log2e;
             if (j > 0) fold_o(j - 1);
             alpha_pending = alpha;
-            float sum = 0.f;
+            // pass 2: P = 2^(s*c - m*c) with the packed 16-bit MUFU (two exponentials per instruction), written straight to
+            // shared memory in the K-major / 128B-swizzled A-operand layout
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint32_t a[32], b[32];
@@ -505,22 +508,21 @@ attn_tc2_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
                     uint32_t packed[16];
 #pragma unroll
                     for (int i = 0; i < 32; i += 2) {
-                        float s0 = __uint_as_float(half == 0 ? a[i] : b[i]);
-                        float s1 = __uint_as_float(half == 0 ? a[i + 1] : b[i + 1]);
-                        float p0 = ex2_approx(fmaf(s0, p.scale_log2e, -mb));
-                        float p1 = ex2_approx(fmaf(s1, p.scale_log2e, -mb));
+                        float x0 = fmaf(__uint_as_float(half == 0 ? a[i] : b[i]), p.scale_log2e, -mb);
+                        float x1 = fmaf(__uint_as_float(half == 0 ? a[i + 1] : b[i + 1]), p.scale_log2e, -mb);
                         if (!full_tile) {
-                            if (kbase + h * 64 + half * 32 + i >= p.Nk) p0 = 0.f;
-                            if (kbase + h * 64 + half * 32 + i + 1 >= p.Nk) p1 = 0.f;
+                            if (kbase + h * 64 + half * 32 + i >= p.Nk) x0 = -INFINITY;
+                            if (kbase + h * 64 + half * 32 + i + 1 >= p.Nk) x1 = -INFINITY;
                         }
-                        sum += p0 + p1;
+                        uint32_t pk;
                         if constexpr (std::is_same<T, __half>::value) {
-                            __half2 hh = __floats2half2_rn(p0, p1);
-                            packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                            asm("{\n\t.reg .b32 t;\n\tcvt.rn.f16x2.f32 t, %2, %1;\n\tex2.approx.f16x2 %0, t;\n\t}"
+                                : "=r"(pk) : "f"(x0), "f"(x1));
                         } else {
-                            __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
-                            packed[i >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+                            asm("{\n\t.reg .b32 t;\n\tcvt.rn.bf16x2.f32 t, %2, %1;\n\tex2.approx.ftz.bf16x2 %0, t;\n\t}"
+                                : "=r"(pk) : "f"(x0), "f"(x1));
                         }
+                        packed[i >> 1] = pk;
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -530,8 +532,13 @@ attn_tc2_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
                     }
                 }
             }
-            l_run = l_run * alpha + sum;
             m_run = m_new;
+            if (g == 0) {  // the "ones" column D of this stage's V tile (row = key r): O[:, D] = sum_j P[:, j]
+                unsigned char* vt = smem + KV_OFF + (j % STAGES) * KV_BYTES + OP_BYTES + (D >> 6) * ATOM_BYTES;
+                const int chunk = ((D & 63) >> 3) ^ (r & 7);
+                *reinterpret_cast<uint16_t*>(vt + r * 128 + chunk * 16 + (D & 7) * 2) =
+                    std::is_same<T, __half>::value ? (uint16_t)0x3C00 : (uint16_t)0x3F80;
+            }
             tc_fence_before();
             fence_async_smem();
             mbar_arrive(&p_full[g]);
@@ -539,7 +546,7 @@ attn_tc2_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         fold_o(ntiles - 1);
         const int q = q0 + g * 128 + r;
         if (q < p.Nq) {
-            const float inv = 1.f / l_run;
+            const float inv = 1.f / o_acc[D];
             T* dst = reinterpret_cast<T*>(p.out) + ((long)row * p.Nq + q) * p.ldo + head * p.d;
 #pragma unroll
             for (int c = 0; c < D; c += 8) {

@@ -81,7 +81,7 @@ struct Smem {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_BYTES = 4 * 128 * 64;  // 2 epilogue groups x 2 buffers x [128 rows x 32 cols] 16-bit
+    static constexpr int EPI_BYTES = 8 * 2 * 32 * 64;  // 8 epilogue warps x 2 buffers x [32 rows x 32 cols] 16-bit
     static constexpr int STAGES = (168 * 1024) / STAGE_BYTES > 6 ? 6 : (168 * 1024) / STAGE_BYTES;
     static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
     static constexpr int BAR_OFF = EPI_OFF + EPI_BYTES;
@@ -189,16 +189,14 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
         }
     } else {
-        // ===== epilogue: warps 2..9.  TMEM lane quarter = warp % 4; the two 4-warp groups alternate 32-col chunks.
-        // Each group stages its [128 x 32] (GEGLU: [128 x 16]) 16-bit chunk in shared memory and one elected thread writes
-        // it with a TMA store (coalesced 128-B lines, rows/cols beyond M/N clipped by the tensor map).
+        // ===== epilogue: warps 2..9.  TMEM lane quarter = warp % 4; the two warps of a quarter alternate 32-col chunks.
+        // Every warp owns a private double-buffered [32 rows x 32 cols] 16-bit staging tile and writes it with its own TMA
+        // store (box 32 x 32; rows/cols beyond M/N are clipped by the tensor map): no cross-warp barrier in the epilogue.
         const int quarter = warp & 3;
         const int half = (warp - 2) >> 2;
-        const bool elected = quarter == 0 && lane == 0;
         const T* bias = reinterpret_cast<const T*>(p.bias);
         const T* res = reinterpret_cast<const T*>(p.residual);
-        unsigned char* stage_base = smem + S::EPI_OFF + half * (2 * 128 * 64);
-        const int row_in_tile = quarter * 32 + lane;
+        unsigned char* stage_base = smem + S::EPI_OFF + (warp - 2) * (2 * 32 * 64);
         int li = 0, chunk_ctr = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
             const int tile = item % (p.tiles_m * p.tiles_n), split = item / (p.tiles_m * p.tiles_n);
@@ -207,7 +205,7 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int buf = li & 1;
             mbar_wait(&acc_full[buf], (li >> 1) & 1);
             tc_fence_after();
-            const long m = m0 + row_in_tile;
+            const long m = m0 + quarter * 32 + lane;
             const bool row_ok = m < p.M;
             const uint32_t tacc = tmem_base + (uint32_t)buf * S::ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
@@ -215,7 +213,7 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 float v[32];
                 tmem_ld32(tacc + (uint32_t)c0, v);  // warp-collective
                 const int n = n0 + c0;
-                if (n >= p.N) continue;             // uniform across the group
+                if (n >= p.N) continue;             // warp-uniform
                 if (p.partial) {  // split-K: raw fp32 partial sums, epilogue happens in splitk_reduce_k
                     if (row_ok) {
                         float* dst = p.partial + ((long)split * p.M + m) * p.N + n;
@@ -250,13 +248,13 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         for (int i = 0; i < 8; ++i) v[j + i] += r8[i];
                     }
                 }
-                // ---- stage + TMA store ----
-                unsigned char* sbuf = stage_base + (chunk_ctr & 1) * (128 * 64);
-                if (elected) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // buffer used 2 chunks ago is free
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
+                // ---- stage in this warp's private buffer, then TMA store ----
+                unsigned char* sbuf = stage_base + (chunk_ctr & 1) * (32 * 64);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // buffer used 2 chunks ago is free
+                __syncwarp();
                 if (p.geglu) {
                     float o8[8];
-                    T* dst = reinterpret_cast<T*>(sbuf + row_in_tile * 32);
+                    T* dst = reinterpret_cast<T*>(sbuf + lane * 32);
 #pragma unroll
                     for (int j = 0; j < 16; j += 8) {
 #pragma unroll
@@ -264,7 +262,7 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         store8<T>(dst + j, o8);
                     }
                 } else {
-                    T* dst = reinterpret_cast<T*>(sbuf + row_in_tile * 64);
+                    T* dst = reinterpret_cast<T*>(sbuf + lane * 64);
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         float o8[8];
@@ -274,11 +272,11 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + half) : "memory");
-                if (elected) {
+                __syncwarp();
+                if (lane == 0) {
                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                                      reinterpret_cast<uint64_t>(&tmC)),
-                                 "r"(smem_u32(sbuf)), "r"(p.geglu ? n / 2 : n), "r"((int)m0)
+                                 "r"(smem_u32(sbuf)), "r"(p.geglu ? n / 2 : n), "r"((int)(m0 + quarter * 32))
                                  : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
@@ -288,7 +286,7 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        if (elected) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -433,7 +431,7 @@ void gemm_tc(const GemmArgs& a0, void* ws, size_t ws_bytes, cudaStream_t s) {
         const int n_out = a.geglu ? a.N / 2 : a.N;
         uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)a.M};
         uint64_t str[1] = {(uint64_t)a.ldc * 2};
-        uint32_t box[2] = {(uint32_t)(a.geglu ? 16 : 32), (uint32_t)BM};
+        uint32_t box[2] = {(uint32_t)(a.geglu ? 16 : 32), 32};  // one warp's sub-tile
         tmC = make_tmap_16bit(a.C, a.dtype, 2, dims, str, box, /*swizzle128=*/false);
     }
     // split-K for the low-resolution layers (few output tiles, K up to 23040): fill the SMs with K slices, fp32

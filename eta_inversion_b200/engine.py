@@ -189,7 +189,9 @@ class UNetEngine:
             raise RuntimeError(f"etai: context must be [B,{self.ctx_len},{self.cross_dim}], got {tuple(ctx.shape)}")
         with torch.cuda.device(self.device):
             check(self._lib.etai_unet_set_context(self._h, ptr(ctx), dtype_code(ctx.dtype), ctx.shape[0], stream_ptr()))
-        self._ctx_key = (ctx.data_ptr(), ctx._version, tuple(ctx.shape), ctx.dtype)
+        # keep a strong reference: comparing (data_ptr, version) alone is unsafe, a freed context's address can be handed
+        # to the next prompt's context by the caching allocator
+        self._ctx_key = (ctx, ctx._version)
 
     def forward(self, sample: torch.Tensor, timestep, encoder_hidden_states: Optional[torch.Tensor] = None,
                 control: Optional[AttnControl] = None, **kwargs) -> UNetOutput:
@@ -199,8 +201,8 @@ class UNetEngine:
             raise RuntimeError(f"etai: sample must be [B,4,{self.latent_hw},{self.latent_hw}], got {tuple(sample.shape)}")
         if encoder_hidden_states is not None:
             ctx = encoder_hidden_states if encoder_hidden_states.is_contiguous() else encoder_hidden_states.contiguous()
-            key = (ctx.data_ptr(), ctx._version, tuple(ctx.shape), ctx.dtype)
-            if key != self._ctx_key:  # the context is constant over a loop; re-project only when it changed
+            k = self._ctx_key
+            if k is None or k[0] is not ctx or k[1] != ctx._version:  # constant over a loop: re-project only on change
                 self.set_context(ctx)
         t = float(timestep.item() if torch.is_tensor(timestep) else timestep)
         ctrl = control if control is not None else self.control

@@ -168,10 +168,11 @@ class DiffusionInversion:
 
     def _ctx_half(self, context: torch.Tensor, half: int) -> torch.Tensor:
         # stable slice object per (context, half) so the engine's projected-K/V cache survives the loop
-        key = (context.data_ptr(), context._version, half)
-        if getattr(self, "_ctx_half_key", None) != key:
+        k = getattr(self, "_ctx_half_key", None)
+        if k is None or k[0] is not context or k[1] != context._version or k[2] != half:
             n = context.shape[0] // 2
-            self._ctx_half_key, self._ctx_half_val = key, context[half * n:(half + 1) * n].contiguous()
+            self._ctx_half_key = (context, context._version, half)  # strong ref: addresses get reused across edits
+            self._ctx_half_val = context[half * n:(half + 1) * n].contiguous()
         return self._ctx_half_val
 
     def predict_noise(self, latent: torch.Tensor, t, context: torch.Tensor, guidance_scale, is_fwd: bool = False,

@@ -39,9 +39,11 @@ class PnPForward:
 
     def __call__(self, unet, sample: torch.Tensor, timestep, encoder_hidden_states: torch.Tensor, control=None):
         assert sample.shape[0] == 4 and encoder_hidden_states.shape[0] == 4
-        key = (encoder_hidden_states.data_ptr(), encoder_hidden_states._version)
-        if key != self._ctx_src:  # slice the context once per loop so the engine keeps its K/V projection cache
-            self._ctx_src, self._ctx3 = key, encoder_hidden_states[[0, 1, 3]].contiguous()
+        src = self._ctx_src
+        if src is None or src[0] is not encoder_hidden_states or src[1] != encoder_hidden_states._version:
+            # slice the context once per loop so the engine keeps its K/V projection cache
+            self._ctx_src = (encoder_hidden_states, encoder_hidden_states._version)
+            self._ctx3 = encoder_hidden_states[[0, 1, 3]].contiguous()
         eps3 = unet(sample[[0, 1, 3]].contiguous(), timestep, encoder_hidden_states=self._ctx3,
                     control=self.control(int(timestep)))["sample"]
         return eps3[[0, 1, 0, 2]]
