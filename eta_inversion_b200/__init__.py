@@ -19,6 +19,7 @@ from .inversion.diffusion_inversion import DiffusionInversion
 from .inversion.direct_inversion import DirectInversion
 from .inversion.eta_inversion import EtaInversion
 from .inversion.negative_prompt_inversion import NegativePromptInversion
+from .inversion.proximal_negative_prompt_inversion import ProximalNegativePromptInversion
 from .models import StablePostProc, StablePreprocess, load_diffusion_model  # noqa: F401
 
 __version__ = "0.1.0"
@@ -36,7 +37,7 @@ _inverters = {
     "dirinv": DirectInversion,
     "etainv": EtaInversion,
     "nti": _out_of_scope("nti", "needs the UNet dgrad path"),
-    "proxnpi": _out_of_scope("proxnpi", "needs the quantile/threshold kernel"),
+    "proxnpi": ProximalNegativePromptInversion,
     "edict": _out_of_scope("edict", "coupled-latent scheduler is outside the hot-path scope"),
     "ddpminv": _out_of_scope("ddpminv", "DDPM inverse scheduler is outside the hot-path scope"),
     "cyclediff": _out_of_scope("cyclediff", "DDPM inverse scheduler is outside the hot-path scope"),

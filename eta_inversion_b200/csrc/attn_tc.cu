@@ -14,6 +14,7 @@
 //                 folds it into the fp32 running output with the deferred rescale factor.
 // S is double buffered in TMEM (2 x 128 columns) so QK^T of tile j+1 overlaps the softmax of tile j; O_j uses
 // d_pad columns at column 256.  The (q,k,v) row remap carries PtP self-replacement / MasaCtrl / PnP (see etai.h).
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 #include "ops.cuh"
@@ -514,14 +515,12 @@ attn_tc2_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
                             if (kbase + h * 64 + half * 32 + i >= p.Nk) x0 = -INFINITY;
                             if (kbase + h * 64 + half * 32 + i + 1 >= p.Nk) x1 = -INFINITY;
                         }
-                        uint32_t pk;
-                        if constexpr (std::is_same<T, __half>::value) {
-                            asm("{\n\t.reg .b32 t;\n\tcvt.rn.f16x2.f32 t, %2, %1;\n\tex2.approx.f16x2 %0, t;\n\t}"
-                                : "=r"(pk) : "f"(x0), "f"(x1));
-                        } else {
-                            asm("{\n\t.reg .b32 t;\n\tcvt.rn.bf16x2.f32 t, %2, %1;\n\tex2.approx.ftz.bf16x2 %0, t;\n\t}"
-                                : "=r"(pk) : "f"(x0), "f"(x1));
-                        }
+                        uint32_t pk;  // (the packed ex2.approx.f16x2 form compiles to two MUFU ops plus a PRMT: no gain)
+                        const float e0 = ex2_approx(x0), e1 = ex2_approx(x1);
+                        if constexpr (std::is_same<T, __half>::value)
+                            asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(pk) : "f"(e0), "f"(e1));
+                        else
+                            asm("cvt.rn.bf16x2.f32 %0, %2, %1;" : "=r"(pk) : "f"(e0), "f"(e1));
                         packed[i >> 1] = pk;
                     }
 #pragma unroll
@@ -574,10 +573,294 @@ void launch_attn2(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap&
     KERNEL_CHECK();
 }
 
-CUtensorMap head_tmap(const void* base, int dtype, int d, int heads, int N, int B, long ld) {
+
+constexpr int AT3_THREADS = 384;  // warpgroup 0: warp 0 TMA, warps 1-2 UMMA issue, warp 3 idle; warpgroups 1, 2: softmax of query tiles 0, 1
+
+// ---------------------------------------------------------------------------------------------------------------
+// d = 40 flash self-attention (64x64 layers), v5.  Profile of the earlier variants (ncu source view, B200): the softmax
+// warps spent 40-60 % of their time in mbarrier waits -- on S_j when S is single-buffered, on O_{j-1} when one thread
+// issues the UMMAs of both query tiles (head-of-line blocking: tile 0's PV waits behind tile 1's P).  This version removes
+// every wait from the steady state:
+//   * 64-key tiles, S double-buffered per query tile (S_{j+2} is issued as soon as P_j is published);
+//   * P double-buffered in shared memory (P_j may be written while PV_{j-1} still reads P_{j-1}; PV_{j-2} is known to
+//     be complete because S_j, issued after it by the same thread, is);
+//   * O accumulates in TMEM across tiles and is rescaled lazily: the running maximum is only raised when it grew by
+//     more than 2^8 (P stays <= 256, exact in fp16/bf16 relative precision; the row sum shares the stale maximum
+//     through the "ones" column, so the result is the same softmax), so the O read-modify-write is off the common path;
+//   * one UMMA-issuing thread per query tile with descriptors reduced to one add per k-step.
+// TMEM: S[g][b] 64 columns at g*128 + b*64, O[g] at 256 + g*64.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// UMMA with descriptors given as (low word, shared high word); ACC is compile-time so no predicate has to be computed
+template <bool ACC>
+__device__ __forceinline__ void umma_lohi(uint32_t d, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc) {
+    if constexpr (ACC)
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "setp.eq.u32 p, %4, %4;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+            "setp.ne.u32 p, %4, %4;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+            ::"r"(d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc) : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(AT3_THREADS, 1)
+attn_d40_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AtParams p) {
+    constexpr int STAGES = 4, D = 40, DPAD = 48, BK4 = 64;
+    constexpr int Q_BYTES = ATOM_BYTES;               // [128 q][64]
+    constexpr int KT_BYTES = BK4 * 128;                // one K or V tile: [64 keys][128 B]
+    constexpr int KV_BYTES = 2 * KT_BYTES;
+    constexpr int KV_OFF = 2 * Q_BYTES, P_OFF = KV_OFF + STAGES * KV_BYTES;   // P[g][b]: [128 q][64 keys] = one atom
+    constexpr int BAR_OFF = P_OFF + 4 * ATOM_BYTES;
+    constexpr float RESCALE_LOG2 = 8.f;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
+    uint64_t* kv_full = q_full + 1;
+    uint64_t* kv_empty = kv_full + STAGES;
+    uint64_t* s_full = kv_empty + STAGES;  // [g][b]
+    uint64_t* p_full = s_full + 4;         // [g][b]
+    uint64_t* o_full = p_full + 4;         // [g]: one phase per PV_j (only the lazy rescale waits on it)
+    uint64_t* o_done = o_full + 2;         // [g]: last PV complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 256, head = blockIdx.y, row = blockIdx.z;
+    const int ntiles = (p.Nk + BK4 - 1) / BK4;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }
+        for (int i = 0; i < 4; ++i) mbar_init(&s_full[i], 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&p_full[i], 128);
+        for (int g = 0; g < 2; ++g) { mbar_init(&o_full[g], 1); mbar_init(&o_done[g], 1); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == 0 && lane == 0) {
+            mbar_expect_tx(q_full, 2 * Q_BYTES);
+            tma_load_4d(smem, &tmQ, q_full, 0, head, q0, p.map.q[row]);
+            tma_load_4d(smem + Q_BYTES, &tmQ, q_full, 0, head, q0 + 128, p.map.q[row]);
+            for (int j = 0; j < ntiles; ++j) {
+                int s = j % STAGES;
+                mbar_wait(&kv_empty[s], ((j / STAGES) & 1) ^ 1);
+                mbar_expect_tx(&kv_full[s], KV_BYTES);
+                unsigned char* kb = smem + KV_OFF + s * KV_BYTES;
+                tma_load_4d(kb, &tmK, &kv_full[s], 0, head, j * BK4, p.map.k[row]);
+                tma_load_4d(kb + KT_BYTES, &tmV, &kv_full[s], 0, head, j * BK4, p.map.v[row]);
+            }
+        } else if ((warp == 1 || warp == 2) && lane == 0) {
+            // ===== UMMA issuer of query tile g: S_j = Q_g K_j^T (3 k-steps of 16), O_g += P_j V_j (4 k-steps) =====
+            const int g = warp - 1;
+            const uint32_t idesc_s = make_idesc_f16(p.fmt, BQ, BK4);
+            const uint32_t idesc_o = make_idesc_f16_bmn(p.fmt, BQ, DPAD);
+            const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 B | version | SWIZZLE_128B
+            const uint32_t lo_k = 1u << 16;                                        // K-major: LBO unused (1)
+            const uint32_t lo_mn = (uint32_t)(KT_BYTES >> 4) << 16;                // MN-major V: single 64-wide N atom
+            const uint32_t q_lo = lo_k | ((smem_u32(smem + g * Q_BYTES) & 0x3FFFF) >> 4);
+            const uint32_t p_lo = lo_k | ((smem_u32(smem + P_OFF + g * 2 * ATOM_BYTES) & 0x3FFFF) >> 4);
+            const uint32_t kv_lo = (smem_u32(smem + KV_OFF) & 0x3FFFF) >> 4;
+            const uint32_t tS = tmem_base + (uint32_t)g * 128, tO = tmem_base + 256 + (uint32_t)g * 64;
+            auto issue_s = [&](int j) {
+                mbar_wait(&kv_full[j % STAGES], (j / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t k_lo = lo_k | (kv_lo + (uint32_t)(j % STAGES) * (KV_BYTES >> 4));
+                const uint32_t d = tS + (uint32_t)(j & 1) * 64;
+                umma_lohi<false>(d, q_lo, k_lo, hi, idesc_s);
+                umma_lohi<true>(d, q_lo + 2, k_lo + 2, hi, idesc_s);
+                umma_lohi<true>(d, q_lo + 4, k_lo + 4, hi, idesc_s);
+                umma_commit(&s_full[g * 2 + (j & 1)]);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            if (ntiles > 1) issue_s(1);
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j % STAGES;
+                mbar_wait(&p_full[g * 2 + (j & 1)], (j >> 1) & 1);
+                tc_fence_after();
+                const uint32_t a_lo = p_lo + (uint32_t)(j & 1) * (ATOM_BYTES >> 4);
+                const uint32_t v_lo = lo_mn | (kv_lo + (uint32_t)s * (KV_BYTES >> 4) + (KT_BYTES >> 4));
+                if (j == 0) umma_lohi<false>(tO, a_lo, v_lo, hi, idesc_o);
+                else umma_lohi<true>(tO, a_lo, v_lo, hi, idesc_o);
+                umma_lohi<true>(tO, a_lo + 2, v_lo + 128, hi, idesc_o);   // 16 keys: +32 B in P's row, +16 rows of V
+                umma_lohi<true>(tO, a_lo + 4, v_lo + 256, hi, idesc_o);
+                umma_lohi<true>(tO, a_lo + 6, v_lo + 384, hi, idesc_o);
+                umma_commit(&kv_empty[s]);  // count 2: both issuers are done with K_j / V_j
+                umma_commit(&o_full[g]);
+                if (j == ntiles - 1) umma_commit(&o_done[g]);
+                if (j + 2 < ntiles) issue_s(j + 2);  // S buffer (j & 1) was consumed before P_j was published
+            }
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+        const int g = (warp - 4) >> 2;
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const uint32_t o_addr = tmem_base + 256 + (uint32_t)g * 64 + lane_addr;
+        const uint32_t p_row = smem_u32(smem + P_OFF + g * 2 * ATOM_BYTES + r * 128);
+        const uint32_t ones_addr = smem_u32(smem + KV_OFF + KT_BYTES + r * 128 + (((D >> 3) ^ (r & 7)) * 16) + (D & 7) * 2);
+        const uint16_t one = std::is_same<T, __half>::value ? (uint16_t)0x3C00 : (uint16_t)0x3F80;
+        float m_run = -INFINITY;
+        const float c = p.scale_log2e;
+
+        for (int j = 0; j < ntiles; ++j) {
+            mbar_wait(&s_full[g * 2 + (j & 1)], (j >> 1) & 1);
+            tc_fence_after();
+            const uint32_t s_addr = tmem_base + (uint32_t)g * 128 + (uint32_t)(j & 1) * 64 + lane_addr;
+            const int kbase = j * BK4;
+            uint32_t sv[64];
+            {
+                uint32_t(&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[0]);
+                uint32_t(&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sv[32]);
+                tmem_ld32_nowait(s_addr, s0);
+                tmem_ld32_nowait(s_addr + 32, s1);
+                tmem_wait_ld();
+            }
+            if (kbase + BK4 > p.Nk) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i)
+                    if (kbase + i >= p.Nk) sv[i] = 0xff800000u;  // -inf
+            }
+            float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int i = 0; i < 64; i += 8) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    mx[k] = fmaxf(mx[k], fmaxf(__uint_as_float(sv[i + 2 * k]), __uint_as_float(sv[i + 2 * k + 1])));
+            }
+            const float m_new = fmaxf(fmaxf(m_run, fmaxf(mx[0], mx[1])), fmaxf(mx[2], mx[3]));
+            if (j == 0) {
+                m_run = m_new;  // O is written (not accumulated) by PV_0
+            } else {
+                const bool grow = (m_new - m_run) * c > RESCALE_LOG2;
+                if (__any_sync(0xffffffffu, grow)) {  // rare after the first tiles: rescale this warp's 32 O rows in TMEM
+                    const float alpha = grow ? ex2_approx((m_run - m_new) * c) : 1.f;
+                    if (grow) m_run = m_new;
+                    mbar_wait(&o_full[g], (j - 1) & 1);  // PV_{j-1} complete; PV_j is not issued before our p_full arrive
+                    tc_fence_after();
+                    uint32_t o0[32], o1[16];
+                    tmem_ld32_nowait(o_addr, o0);
+                    tmem_ld16_nowait(o_addr + 32, o1);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) o0[i] = __float_as_uint(__uint_as_float(o0[i]) * alpha);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) o1[i] = __float_as_uint(__uint_as_float(o1[i]) * alpha);
+                    tmem_st32(o_addr, o0);
+                    tmem_st16(o_addr + 32, o1);
+                    tmem_wait_st();
+                }
+            }
+            const float mb = m_run * c;
+            // P_j = 2^(s*c - m*c) -> 16-bit, swizzled A-operand tile, buffer j & 1
+            const uint32_t p_dst = p_row + (uint32_t)(j & 1) * ATOM_BYTES;
+#pragma unroll
+            for (int blk = 0; blk < 8; ++blk) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float e0 = ex2_approx(fmaf(__uint_as_float(sv[blk * 8 + 2 * e]), c, -mb));
+                    const float e1 = ex2_approx(fmaf(__uint_as_float(sv[blk * 8 + 2 * e + 1]), c, -mb));
+                    if constexpr (std::is_same<T, __half>::value)
+                        asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(pk[e]) : "f"(e0), "f"(e1));
+                    else
+                        asm("cvt.rn.bf16x2.f32 %0, %2, %1;" : "=r"(pk[e]) : "f"(e0), "f"(e1));
+                }
+                sts128(p_dst + (uint32_t)((blk ^ (r & 7)) * 16), pk[0], pk[1], pk[2], pk[3]);
+            }
+            // "ones" column D of this stage's V tile (row = key r): O[:, D] accumulates sum_j P[:, j].  Both query tiles
+            // write the same value, so neither issuer depends on the other tile's warpgroup.
+            if (r < BK4)
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(ones_addr + (uint32_t)(j % STAGES) * KV_BYTES), "h"(one) : "memory");
+            tc_fence_before();
+            fence_async_smem();
+            mbar_arrive(&p_full[g * 2 + (j & 1)]);
+        }
+        // (o_full cannot be used here: PV of the last TWO tiles may be pending, which a parity wait cannot tell apart)
+        mbar_wait(&o_done[g], 0);
+        tc_fence_after();
+        uint32_t o0[32], o1[16];
+        tmem_ld32_nowait(o_addr, o0);
+        tmem_ld16_nowait(o_addr + 32, o1);
+        tmem_wait_ld();
+        const int q = q0 + g * 128 + r;
+        if (q < p.Nq) {
+            const float inv = 1.f / __uint_as_float(o1[D - 32]);
+            T* dst = reinterpret_cast<T*>(p.out) + ((long)row * p.Nq + q) * p.ldo + head * D;
+#pragma unroll
+            for (int cc = 0; cc < D; cc += 8) {
+                float o8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o8[i] = __uint_as_float(cc + i < 32 ? o0[(cc + i) & 31] : o1[(cc + i) & 15]) * inv;
+                store8<T>(dst + cc, o8);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+template <typename T>
+void launch_attn_d40(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AtParams& p, dim3 grid, cudaStream_t s) {
+    constexpr int SMEM = 2 * ATOM_BYTES + 4 * 2 * 64 * 128 + 4 * ATOM_BYTES + 256 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(attn_d40_k<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured = true;
+    }
+    attn_d40_k<T><<<grid, AT3_THREADS, SMEM, s>>>(q, k, v, p);
+    KERNEL_CHECK();
+}
+
+CUtensorMap head_tmap(const void* base, int dtype, int d, int heads, int N, int B, long ld, int box_rows = 128) {
     uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)N, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)d * 2, (uint64_t)ld * 2, (uint64_t)ld * 2 * N};
-    uint32_t box[4] = {64, 1, 128, 1};
+    uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
     return make_tmap_16bit(base, dtype, 4, dims, str, box);
 }
 
@@ -606,9 +889,14 @@ void attention_tc(const SelfAttnArgs& a, cudaStream_t s) {
     dim3 grid(cdiv(a.Nq, BQ), a.heads, a.B);
     const bool two = a.d != 160 && a.Nq >= 256;  // ping-pong kernel: 256 query rows per CTA
     if (two) grid.x = cdiv(a.Nq, 256);
+    const bool d40 = two && a.d == 40;
+    if (d40) {  // 64-key tiles
+        tk = head_tmap(a.k, a.dtype, a.d, a.heads, a.Nk, a.B, a.ldk, 64);
+        tv = head_tmap(a.v, a.dtype, a.d, a.heads, a.Nk, a.B, a.ldv, 64);
+    }
 #define LAUNCH(T)                                                              \
     do {                                                                       \
-        if (two && a.d == 40) launch_attn2<T, 1, 2>(tq, tk, tv, p, grid, s);   \
+        if (d40) launch_attn_d40<T>(tq, tk, tv, p, grid, s);                   \
         else if (two) launch_attn2<T, 2, 1>(tq, tk, tv, p, grid, s);           \
         else if (a.d == 40) launch_attn<T, 1, 2>(tq, tk, tv, p, grid, s);      \
         else if (a.d == 80) launch_attn<T, 2, 2>(tq, tk, tv, p, grid, s);      \

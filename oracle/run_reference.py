@@ -46,6 +46,7 @@ SCENARIOS = {
     "dirinv_ptp_replace_3": (dict(type="dirinv", scheduler="ddim", num_inference_steps=3), "ptp", {}, PTP_REPLACE, None),
     "npi_simple_3": (dict(type="npi", scheduler="ddim", num_inference_steps=3), "simple", {}, None, None),
     "diffinv_pnp_5": (dict(type="diffinv", scheduler="ddim", num_inference_steps=5), "pnp", {}, None, None),
+    "proxnpi_simple_3": (dict(type="proxnpi", scheduler="ddim", num_inference_steps=3), "simple", {}, None, None),
 }
 
 

@@ -64,3 +64,5 @@ def test_registry_surface_matches_reference():
     assert set(etai.get_edit_methods()) == {"simple", "ptp", "masactrl", "pnp", "pix2pix_zero", "invedit"}
     with pytest.raises(NotImplementedError):
         etai.load_inverter(type="edict", model=None)
+    with pytest.raises(NotImplementedError):
+        etai.load_inverter(type="nti", model=None)

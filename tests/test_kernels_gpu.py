@@ -167,6 +167,30 @@ def test_attention_tc(dtype, N, d):
     assert err < (4e-3 if dtype == torch.float16 else 2e-2)
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N", [4096, 1000])
+def test_attention_tc_growing_logits(dtype, N):
+    """Keys whose magnitude ramps up along the sequence: the running row maximum keeps growing by more than the lazy
+    rescale threshold (2^8), so the in-TMEM rescale of the d = 40 kernel runs many times per row, on some rows only."""
+    from eta_inversion_b200 import engine as E
+    B, heads, d = 2, 8, 40
+    C = heads * d
+    g = torch.Generator().manual_seed(7)
+    q = torch.randn((B, N, C), generator=g)
+    k = torch.randn((B, N, C), generator=g) * torch.linspace(0.2, 14.0, N).reshape(1, N, 1)
+    k[:, :, :C // 2] *= 0.1  # half of the heads stay flat: no rescale there
+    v = torch.randn((B, N, C), generator=g)
+    q, k, v = (t.to(dtype).cuda() for t in (q, k, v))
+    out = E.attention(q, k, v, heads)
+
+    def sh(t):
+        return t.float().reshape(B, N, heads, d).permute(0, 2, 1, 3)
+    ref = F.scaled_dot_product_attention(sh(q), sh(k), sh(v)).permute(0, 2, 1, 3).reshape(B, N, C)
+    err = _relerr(out.float(), ref)
+    print(f"attention_tc growing {dtype} N={N}: rel err {err:.2e}")
+    assert err < (4e-3 if dtype == torch.float16 else 2e-2)
+
+
 def test_scheduler_step_matches_closed_form():
     from eta_inversion_b200 import engine as E
     n, Esz = 2, 4 * 64 * 64
