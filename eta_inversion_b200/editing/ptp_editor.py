@@ -35,7 +35,14 @@ class PromptToPromptControllerBase(ControllerBase):
                            resize: Optional[int] = None, prompt_idx: int = 0) -> torch.Tensor:
         """Batched form of get_attention_map: [len(words),1,R,R] maps, each max-normalised (and bicubic-resized)."""
         maps = ptp.aggregate_attention([None], self.controller, res, list(from_where), True, select=prompt_idx)
-        m = maps[:, :, word_indices].permute(2, 0, 1)[:, None]  # [W,1,res,res]
+        # index tensor cached on the device: indexing with a Python list uploads it every call, and that pageable
+        # host-to-device copy synchronises the host with the GPU once per inversion step
+        key = (tuple(word_indices), maps.device)
+        cache = self.__dict__.setdefault("_word_idx_cache", {})
+        idx = cache.get(key)
+        if idx is None:
+            idx = cache[key] = torch.tensor(list(word_indices), dtype=torch.long, device=maps.device)
+        m = maps.index_select(2, idx).permute(2, 0, 1)[:, None]  # [W,1,res,res]
         m = m / m.amax(dim=(1, 2, 3), keepdim=True)
         if resize is not None and m.shape[-2:] != (resize, resize):
             m = F.interpolate(m, (resize, resize), mode="bicubic").clamp(0, 1)

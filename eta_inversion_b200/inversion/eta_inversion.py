@@ -24,6 +24,9 @@ from ..editing.ptp_editor import PromptToPromptControllerAttentionStore
 from .diffusion_inversion import DiffusionInversion
 
 
+_NOISE_TABLES: Dict[Any, torch.Tensor] = {}  # (seed, steps, K, hw, device) -> [steps,K,1,4,hw,hw] candidate noise
+
+
 class ControllerAttentionStorePerStep(PromptToPromptControllerAttentionStore):
     def __init__(self, model, prompt, res, from_where, callback) -> None:
         super().__init__(model, max_size=res)
@@ -88,12 +91,23 @@ class EtaInversion(DiffusionInversion):
     def _noise_for_loop(self, steps: int) -> torch.Tensor:
         if self.noise_provider is not None:
             return torch.stack([self.noise_provider(i) for i in range(steps)]).to(self.model.device, torch.float32)
+        hw = self.unet.latent_hw
+        key = (self.seed, steps, self.noise_sample_count, hw, str(self.model.device))
+        if self.seed is not None and key in _NOISE_TABLES:
+            return _NOISE_TABLES[key]
         g = torch.Generator()
         if self.seed is not None:
             g.manual_seed(self.seed)
-        hw = self.unet.latent_hw
         # one draw for the whole loop == the reference's per-step draws from one generator (numel multiple of 16)
-        return torch.randn((steps, self.noise_sample_count, 1, 4, hw, hw), generator=g).to(self.model.device)
+        table = torch.randn((steps, self.noise_sample_count, 1, 4, hw, hw), generator=g).to(self.model.device)
+        if self.seed is not None:
+            # The reference re-seeds its generator with the same seed on every edit (eta_inversion.py:276), so the
+            # candidate table is a constant of (seed, steps, K): keep the device copy instead of redrawing 8M normals
+            # on the host and uploading 32 MB per edit.  Read-only by contract.
+            if len(_NOISE_TABLES) >= 4:
+                _NOISE_TABLES.pop(next(iter(_NOISE_TABLES)))
+            _NOISE_TABLES[key] = table
+        return table
 
     # ---- masks -----------------------------------------------------------------------------------
     def get_mask(self, key, mask, t, edit_word_idx):
