@@ -76,6 +76,55 @@ struct TcParams {
     int fmt;               // 0 f16, 1 bf16
 };
 
+// ---- epilogue helpers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, uint32_t (&r)[32]) {  // no wait: pair with tmem_wait_ld()
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {  // two fp32 -> packed 16-bit pair (lo in bits 0..15)
+    uint32_t d;
+    if constexpr (std::is_same<T, __half>::value) asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(d) : "f"(lo), "f"(hi));
+    else asm("cvt.rn.bf16x2.f32 %0, %2, %1;" : "=r"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+template <typename T>
+__device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) {  // packed 16-bit add
+    uint32_t d;
+    if constexpr (std::is_same<T, __half>::value) asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    else asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// erf-form GELU for 16-bit outputs: Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below the output rounding) with
+// one rcp and one ex2 instead of erff's two-range polynomial (the GEGLU epilogue is issue-bound on the K = 320 layers)
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+    const float erf_abs = fmaf(-poly, e, 1.0f);
+    return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+
 template <int BN>
 struct Smem {
     static constexpr int A_BYTES = BM * BK * 2;
@@ -208,6 +257,93 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const long m = m0 + quarter * 32 + lane;
             const bool row_ok = m < p.M;
             const uint32_t tacc = tmem_base + (uint32_t)buf * S::ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
+            // ---- lean paths (the bulk of the UNet's GEMMs).  For K = 320..640 the main loop of a tile is < 1 us and the
+            // epilogue sets the pace; it is bound by instruction latency with two warps per scheduler, so: operands stay
+            // packed (one F2FP per pair, packed adds), bias / residual loads are issued under the TMEM load, staging
+            // goes through st.shared.v4, and address arithmetic is hoisted out of the chunk loop.
+            if (!p.partial && !p.bias2) {
+                const uint32_t sbase = smem_u32(stage_base) + (uint32_t)lane * (p.geglu ? 32u : 64u);
+                const T* brow = bias ? bias + n0 : nullptr;
+                const T* rrow = (res && row_ok && !p.geglu) ? res + m * p.ldr + n0 : nullptr;
+#pragma unroll 1
+                for (int c0 = half * 32; c0 < BN; c0 += 64) {
+                    uint32_t r[32];
+                    tmem_ld32_raw(tacc + (uint32_t)c0, r);  // warp-collective
+                    const bool col_ok = n0 + c0 < p.N;      // warp-uniform
+                    uint4 b4[4], r4[4];
+                    if (col_ok && brow) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) b4[j] = ldg128(brow + c0 + 8 * j);
+                    }
+                    if (col_ok && rrow) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) r4[j] = ldg128(rrow + c0 + 8 * j);
+                    }
+                    tmem_wait_ld();
+                    if (!col_ok) continue;
+                    const uint32_t sbuf = sbase + (uint32_t)(chunk_ctr & 1) * (32 * 64);
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // buffer used 2 chunks ago is free
+                    __syncwarp();
+                    if (p.geglu) {
+                        // (value, gate) column pairs; bias in fp32 (it feeds the nonlinearity)
+                        uint32_t h[8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float bf[8];
+                            if (brow) {
+                                const Pack<T, 8>& pk = *reinterpret_cast<const Pack<T, 8>*>(&b4[j]);
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) bf[i] = to_f<T>(pk.v[i]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) bf[i] = 0.f;
+                            }
+                            float o[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                o[i] = (__uint_as_float(r[8 * j + 2 * i]) + bf[2 * i]) *
+                                       gelu_fast(__uint_as_float(r[8 * j + 2 * i + 1]) + bf[2 * i + 1]);
+                            h[2 * j] = pack2<T>(o[0], o[1]);
+                            h[2 * j + 1] = pack2<T>(o[2], o[3]);
+                        }
+                        sts128(sbuf, h[0], h[1], h[2], h[3]);
+                        sts128(sbuf + 16, h[4], h[5], h[6], h[7]);
+                    } else {
+                        uint32_t h[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) h[i] = pack2<T>(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                        if (brow) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                h[4 * j] = add2<T>(h[4 * j], b4[j].x); h[4 * j + 1] = add2<T>(h[4 * j + 1], b4[j].y);
+                                h[4 * j + 2] = add2<T>(h[4 * j + 2], b4[j].z); h[4 * j + 3] = add2<T>(h[4 * j + 3], b4[j].w);
+                            }
+                        }
+                        if (rrow) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                h[4 * j] = add2<T>(h[4 * j], r4[j].x); h[4 * j + 1] = add2<T>(h[4 * j + 1], r4[j].y);
+                                h[4 * j + 2] = add2<T>(h[4 * j + 2], r4[j].z); h[4 * j + 3] = add2<T>(h[4 * j + 3], r4[j].w);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) sts128(sbuf + 16 * j, h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int n = n0 + c0;
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                         reinterpret_cast<uint64_t>(&tmC)),
+                                     "r"(sbuf - (uint32_t)lane * (p.geglu ? 32u : 64u)), "r"(p.geglu ? n / 2 : n),
+                                     "r"((int)(m0 + quarter * 32))
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++chunk_ctr;
+                }
+            } else
+            // ---- generic path: split-K partials, fp32 time-embedding bias (resnet conv1) ----
 #pragma unroll 1
             for (int c0 = half * 32; c0 < BN; c0 += 64) {
                 float v[32];

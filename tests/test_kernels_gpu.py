@@ -71,6 +71,34 @@ def test_gemm_tc_geglu(dtype):
     assert _relerr(out.float(), ref) < TOL[dtype]
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(20077, 320, 640), (9900, 960, 320), (37 * 256 + 1, 320, 64), (16384, 1280, 1280)])
+def test_gemm_tc_large(dtype, M, N, K):
+    """Many tiles per persistent CTA (several rounds of the double-buffered accumulator), ragged M tails."""
+    from eta_inversion_b200 import engine as E
+    A, W = _rand((M, K), 1).to(dtype).cuda(), _rand((N, K), 2, K ** -0.5).to(dtype).cuda()
+    b, r = _rand((N,), 3).to(dtype).cuda(), _rand((M, N), 4).to(dtype).cuda()
+    out = E.gemm(A, W, b, r)
+    ref = A.float() @ W.float().T + b.float() + r.float()
+    assert _relerr(out.float(), ref) < TOL[dtype]
+    # per-row check on the first / last rows of tiles
+    for m in (0, 127, 128, 255, M - 1, M - 130 if M > 130 else 0):
+        assert _relerr(out[m].float(), ref[m]) < 4 * TOL[dtype]
+
+
+def test_gemm_tc_large_geglu():
+    from eta_inversion_b200 import engine as E
+    dtype = torch.float16
+    M, C = 8192, 320
+    A, W, b = _rand((M, C), 1).to(dtype).cuda(), _rand((8 * C, C), 2, C ** -0.5).to(dtype).cuda(), _rand((8 * C,), 3).to(dtype).cuda()
+    Wi = torch.stack([W[:4 * C], W[4 * C:]], 1).reshape(8 * C, C).contiguous()
+    bi = torch.stack([b[:4 * C], b[4 * C:]], 1).reshape(8 * C).contiguous()
+    out = E.gemm(A, Wi, bi, geglu=True)
+    h = A.float() @ W.float().T + b.float()
+    ref = h[:, :4 * C] * F.gelu(h[:, 4 * C:])
+    assert _relerr(out.float(), ref) < TOL[dtype]
+
+
 def _conv_ref(x_nhwc, w_oihw, bias, stride):
     y = F.conv2d(x_nhwc.permute(0, 3, 1, 2).float(), w_oihw.float(), bias.float(), stride=stride, padding=1)
     return y.permute(0, 2, 3, 1).contiguous()
@@ -102,6 +130,24 @@ def test_conv3x3_tc(dtype, B, H, Ci, Co, stride):
     res = _rand(tuple(ref.shape), 5).to(dtype).cuda()
     out = E.conv3x3(x, wp, b, residual=res, stride=stride)
     assert _relerr(out.float(), ref + res.float()) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("B,H,Ci,Co", [(5, 64, 320, 320), (9, 32, 640, 640), (12, 16, 1280, 1280), (40, 8, 1280, 1280),
+                                        (11, 16, 2560, 1280)])
+def test_conv3x3_tc_large(dtype, B, H, Ci, Co):
+    """Implicit-GEMM conv at co-batched sizes (odd image counts: the last 128-pixel box is partly out of range)."""
+    from eta_inversion_b200 import engine as E
+    x = _rand((B, H, H, Ci), 1).to(dtype).cuda()
+    w = _rand((Co, Ci, 3, 3), 2, (9 * Ci) ** -0.5).to(dtype).cuda()
+    b = _rand((Co,), 3).to(dtype).cuda()
+    wp = w.permute(0, 2, 3, 1).contiguous()
+    res = _rand((B, H, H, Co), 5).to(dtype).cuda()
+    out = E.conv3x3(x, wp, b, residual=res)
+    ref = _conv_ref(x, w, b, 1) + res.float()
+    assert _relerr(out.float(), ref) < TOL[dtype]
+    for img in (0, B - 1):
+        assert _relerr(out[img].float(), ref[img]) < 4 * TOL[dtype]
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
