@@ -153,6 +153,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cobatch", type=int, default=4,
                     help="independent edits walked in lock step per step on each GPU (they share every UNet forward)")
+    ap.add_argument("--pipes", type=int, default=2,
+                    help="lock-step groups in flight per GPU, each on its own engine (activation arena, graphs, stream): one "
+                         "group's setup / VAE / host copies overlap the other's UNet forwards")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -168,17 +171,20 @@ def main():
     W = max(args.warmup, 3)
     K = args.steps
 
-    from eta_inversion_b200.batching import run_lockstep
+    from eta_inversion_b200.batching import run_lockstep, run_pipelined
+    from eta_inversion_b200.models import clone_pipeline
     CB = max(1, args.cobatch)
+    G = max(1, args.pipes)  # a step = G groups of CB edits, the groups of all steps are pipelined over G engines
     pipe, (preproc, postproc) = etai.load_diffusion_model("synthetic-sd15", f"cuda:{local}", variant=args.variant,
                                                           max_batch=4 * CB)
+    pipes = [pipe] + [clone_pipeline(pipe) for _ in range(G - 1)]
 
     def make_editor(p):
         inv = etai.load_inverter(type="etainv", model=p, scheduler="ddim", num_inference_steps=args.inv_steps,
                                  guidance_scale_bwd=7.5)
         return etai.load_editor(type="ptp", inverter=inv)
     editor = make_editor(pipe)
-    n_img = (W + K) * CB
+    n_img = (W + K) * CB * G
     host_imgs = [syn.synthetic_image(100000 * rank + i).pin_memory() for i in range(n_img)]
     dev_imgs = [h.cuda(non_blocking=True) for h in host_imgs]
 
@@ -188,7 +194,7 @@ def main():
         torch.cuda.synchronize()
 
     def edit(imgs):
-        """One step = CB independent edits (different images) walked in lock step."""
+        """One lock-step group = CB independent edits (different images) sharing every UNet forward."""
         if CB == 1:
             with torch.no_grad():
                 return [editor.edit(imgs[0], SRC, TGT, cfg={**PTP_CFG}, inv_cfg=INV_CFG)]
@@ -198,40 +204,60 @@ def main():
     def batch(lst, i):
         return lst[i * CB:(i + 1) * CB]
 
+    def steps(imgs, first, count, on_result=None):
+        """`count` steps starting at step `first`: count * G groups, G of them in flight at any time."""
+        groups = [batch(imgs, g) for g in range(first * G, (first + count) * G)]
+        if G == 1:
+            out = []
+            for gi, grp in enumerate(groups):
+                r = edit(grp)
+                out.append(on_result(gi, r) if on_result else r)
+            return out
+        jobs = [[dict(image=im, source_prompt=SRC, target_prompt=TGT, cfg={**PTP_CFG}, inv_cfg=dict(INV_CFG)) for im in grp]
+                for grp in groups]
+        return run_pipelined(pipes, jobs, make_editor, on_result=on_result)
+
+    def launches_now():
+        return sum(p.unet.launch_count for p in pipes) + E.LAUNCHES[0]
+
     # ---- (1) device-resident throughput ----------------------------------------------------------
-    for i in range(W):
-        edit(batch(dev_imgs, i))
+    steps(dev_imgs, 0, W)
     barrier()
-    l0, s0 = pipe.unet.launch_count, E.LAUNCHES[0]
+    l0 = launches_now()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         ev0.record()
-        for i in range(K):
-            edit(batch(dev_imgs, W + i))
+        steps(dev_imgs, W, K)       # returns with every group's stream synchronised
+        torch.cuda.synchronize()
         ev1.record()
         barrier()
-    launches = (pipe.unet.launch_count - l0) + (E.LAUNCHES[0] - s0)
+    launches = launches_now() - l0
     ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
 
     # ---- (2) end to end through the public API with host buffers -----------------------------------
+    d2h_box = [0]
+
+    def to_host(gi, results):
+        n = 0
+        for res in results:
+            out = [postproc(res["image"]), postproc(res["image_inv"])]  # device -> host uint8 images (cv2.imwrite input)
+            n += res["image"].numel() * res["image"].element_size() * 2
+        d2h_box[0] = n * G  # per step
+        return None
+
     barrier()
     t0 = time.perf_counter()
-    d2h = 0
-    for i in range(K):
-        imgs = [h.to(f"cuda:{local}", non_blocking=True) for h in batch(host_imgs, W + i)]
-        d2h = 0
-        for res in edit(imgs):
-            out = [postproc(res["image"]), postproc(res["image_inv"])]  # device -> host uint8 images (cv2.imwrite input)
-            d2h += res["image"].numel() * res["image"].element_size() * 2
+    steps(host_imgs, W, K, on_result=to_host)   # pinned host images: every lane uploads its own inside the region
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device="cuda")
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
-    h2d = host_imgs[0].numel() * host_imgs[0].element_size() * CB
+    d2h = d2h_box[0]
+    h2d = host_imgs[0].numel() * host_imgs[0].element_size() * CB * G
 
     # ---- (2b) share of the step spent inside UNet forwards (graph replay, CUDA events), one more step ----
     pipe.unet.time_forwards(True)
@@ -264,19 +290,20 @@ def main():
     breakdown = {k: {"ms_per_edit": round(v["ms"], 2), "launches": v["launches"],
                      "tflops": round(2.0 * macs[k] * rows / 1e12 / (v["ms"] / 1e3), 1) if k in macs and v["ms"] > 0 else None}
                  for k, v in prof.items()}
-    value = world * K * CB / (ms_total / 1e3)
+    value = world * K * CB * G / (ms_total / 1e3)
     line = {
         "metric": "edits/sec etainv+PtP SD1.5 512^2 50-step", "value": value, "unit": "edits/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.variant, "data": "synthetic",
         "config": {"workload": workload_name(args.inv_steps), "inv_steps": args.inv_steps, "unet_rows_per_edit": rows,
-                   "edits_per_step": CB, "cobatch": f"{CB} independent edits per GPU share each UNet forward (B={2 * CB} inversion, B={4 * CB} edit)",
+                   "edits_per_step": CB * G, "cobatch": f"{CB} independent edits per GPU share each UNet forward (B={2 * CB} inversion, B={4 * CB} edit)",
+                   "pipes": f"{G} lock-step group(s) in flight per GPU, each on its own engine instance (same weights)",
                    "ms_per_unet_forward_avg": round(unet_graph_ms / (2 * args.inv_steps), 3),
                    "unet_share_of_step": round(unet_graph_ms / step_wall_ms, 3),
                    "l2": "no explicit flush: every UNet forward streams 1.72 GB of fp16 weights (>> 126 MB L2)",
                    "parallelism": f"per-image sharding, {world} independent rank(s), no collective in the loop"},
         "clocks": clocks.summary(),
-        "e2e": {"value": world * K * CB / e2e_s, "unit": "edits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": world * K * CB * G / e2e_s, "unit": "edits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": {"conv3x3": "gemm_tc_k<conv>", "gemm": "gemm_tc_k<dense>",
                                                      "self_attn": "attention"}[dom],

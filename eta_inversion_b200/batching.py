@@ -137,8 +137,10 @@ class LockstepGroup:
         return out, scatter
 
 
-def run_lockstep(pipe, jobs: Sequence[Dict[str, Any]], make_editor: Callable[[Any], Any]) -> List[Any]:
-    """Run ``len(jobs)`` edits in lock step on ``pipe``.
+def run_lockstep(pipe, jobs: Sequence[Dict[str, Any]], make_editor: Callable[[Any], Any],
+                 stream: Optional[torch.cuda.Stream] = None) -> List[Any]:
+    """Run ``len(jobs)`` edits in lock step on ``pipe``.  ``stream``: CUDA stream every lane issues its work on
+    (default: each thread's current stream); groups that run concurrently must use different streams.
 
     jobs[i]: kwargs of ``Editor.edit`` (image, source_prompt, target_prompt, cfg, inv_cfg).
     make_editor(lane_pipe) -> editor: builds the lane's own inverter + editor on a per-lane view of the pipeline
@@ -148,10 +150,11 @@ def run_lockstep(pipe, jobs: Sequence[Dict[str, Any]], make_editor: Callable[[An
     k = len(jobs)
     group = LockstepGroup(pipe.unet, k)
     editors = []
-    for l in range(k):
-        lane_pipe = copy.copy(pipe)
-        lane_pipe.unet = group.lane_unet(l)
-        editors.append(make_editor(lane_pipe))
+    with torch.cuda.stream(stream):  # constructors may create device tensors: same stream as the lanes' work
+        for l in range(k):
+            lane_pipe = copy.copy(pipe)
+            lane_pipe.unet = group.lane_unet(l)
+            editors.append(make_editor(lane_pipe))
     results: List[Any] = [None] * k
     errors: List[Optional[BaseException]] = [None] * k
     dev = pipe.device
@@ -159,7 +162,7 @@ def run_lockstep(pipe, jobs: Sequence[Dict[str, Any]], make_editor: Callable[[An
     def work(l: int) -> None:
         try:
             torch.cuda.set_device(dev)
-            with torch.no_grad():
+            with torch.no_grad(), torch.cuda.stream(stream):  # stream=None is a no-op context
                 results[l] = editors[l].edit(**jobs[l])
         except BaseException as e:  # noqa: BLE001
             errors[l] = e
@@ -183,3 +186,47 @@ def run_lockstep(pipe, jobs: Sequence[Dict[str, Any]], make_editor: Callable[[An
         if e is not None:
             raise e
     return results
+
+
+def run_pipelined(pipes: Sequence[Any], job_groups: Sequence[Sequence[Dict[str, Any]]],
+                  make_editor: Callable[[Any], Any],
+                  on_result: Optional[Callable[[int, List[Any]], Any]] = None) -> List[List[Any]]:
+    """Run several lock-step groups with ``len(pipes)`` of them in flight at any time.
+
+    One group alone leaves the GPU idle while its lanes set up (text encoder, VAE encode, controllers: ~160 ms per
+    group of 4), while the host drains the launch queue between the inversion and the editing loop, and during the
+    final VAE decode / device-to-host copy -- about 10 % of a 50-step edit at B200 speed.  Edits are independent
+    (SURVEY.md section 8e), so a second group on its OWN engine (own activation arena, CUDA graphs and stream; weights
+    are read-only) fills those gaps: group g runs on ``pipes[g % len(pipes)]``, each pipe is driven by one thread.
+    Results are returned in ``job_groups`` order.  Tensors in the jobs must be complete before the call (the groups
+    run on side streams that only synchronise with the caller at entry and exit); images may be pinned host tensors
+    (each lane uploads its own).  ``on_result(g, results)`` runs in the driving thread as soon as group g is complete
+    (e.g. device-to-host copies / file writes, which then overlap the other pipe's work); its return value replaces
+    the group's results."""
+    n = len(pipes)
+    out: List[Any] = [None] * len(job_groups)
+    errors: List[Optional[BaseException]] = [None] * n
+    dev = pipes[0].device
+    torch.cuda.synchronize(dev)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(n)]
+
+    def drive(w: int) -> None:
+        try:
+            torch.cuda.set_device(dev)
+            for g in range(w, len(job_groups), n):
+                out[g] = run_lockstep(pipes[w], job_groups[g], make_editor, stream=streams[w])
+                streams[w].synchronize()  # results of group g are complete; its buffers may be reused by group g + n
+                if on_result is not None:
+                    out[g] = on_result(g, out[g])
+        except BaseException as e:  # noqa: BLE001
+            errors[w] = e
+
+    threads = [threading.Thread(target=drive, args=(w,), name=f"etai-pipe-{w}") for w in range(n)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for e in errors:
+        if e is not None:
+            raise e
+    return out

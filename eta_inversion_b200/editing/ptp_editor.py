@@ -11,6 +11,9 @@ from .controller import ControllerBase
 from .editor import ControllerBasedEditor
 
 
+_WORD_IDX_CACHE: Dict[Any, torch.Tensor] = {}  # (token indices, device) -> index tensor on the device
+
+
 class PromptToPromptControllerBase(ControllerBase):
     """Wraps a ptp attention controller; installs its per-step ``AttnControl`` instead of patching 32 modules."""
 
@@ -38,10 +41,13 @@ class PromptToPromptControllerBase(ControllerBase):
         # index tensor cached on the device: indexing with a Python list uploads it every call, and that pageable
         # host-to-device copy synchronises the host with the GPU once per inversion step
         key = (tuple(word_indices), maps.device)
-        cache = self.__dict__.setdefault("_word_idx_cache", {})
-        idx = cache.get(key)
+        idx = _WORD_IDX_CACHE.get(key)
         if idx is None:
-            idx = cache[key] = torch.tensor(list(word_indices), dtype=torch.long, device=maps.device)
+            idx = torch.tensor(list(word_indices), dtype=torch.long, device=maps.device)
+            torch.cuda.current_stream(maps.device).synchronize()  # published to other threads / streams below
+            if len(_WORD_IDX_CACHE) >= 256:
+                _WORD_IDX_CACHE.clear()
+            _WORD_IDX_CACHE[key] = idx
         m = maps.index_select(2, idx).permute(2, 0, 1)[:, None]  # [W,1,res,res]
         m = m / m.amax(dim=(1, 2, 3), keepdim=True)
         if resize is not None and m.shape[-2:] != (resize, resize):

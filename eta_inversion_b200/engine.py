@@ -254,6 +254,15 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias=None, residual=None, s
     return out
 
 
+def h2d(t: torch.Tensor, device) -> torch.Tensor:
+    """Small host tensor -> device without stalling the host: a pageable `.to(device)` waits until the stream has
+    drained (every queued UNet forward), which leaves the GPU idle afterwards while the host catches up; a pinned
+    staging copy is asynchronous (the caching host allocator keeps the staging block alive until the copy has run)."""
+    if t.device.type != "cpu":
+        return t.to(device)
+    return t.pin_memory().to(device, non_blocking=True)
+
+
 def groupnorm(x: torch.Tensor, gamma, beta, groups: int = 32, eps: float = 1e-5, silu: bool = False):
     """x: NHWC [B,HW,C]."""
     _require_cuda(x, "x")

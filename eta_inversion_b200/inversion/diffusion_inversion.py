@@ -13,7 +13,7 @@ from typing import Any, Dict, Iterable, Iterator, List, Optional, Tuple, Union
 import torch
 
 from ..editing.controller import ControllerBase, ControllerEmpty
-from ..engine import AttnControl
+from ..engine import AttnControl, h2d
 from ..inverse_schedulers import DDIMInverseScheduler, DDIMScheduler
 
 
@@ -125,7 +125,7 @@ class DiffusionInversion:
     def _embed_uncached(self, text: str) -> torch.Tensor:
         tok = self.model.tokenizer([text], padding="max_length", max_length=self.model.tokenizer.model_max_length,
                                    truncation=True, return_tensors="pt")
-        return self.model.text_encoder(tok.input_ids.to(self.model.device))[0].float()
+        return self.model.text_encoder(h2d(tok.input_ids, self.model.device))[0].float()
 
     def create_context(self, prompt: str, negative_prompt: str = "") -> torch.Tensor:
         text_embeddings = self._embed(prompt)

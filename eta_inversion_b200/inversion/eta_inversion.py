@@ -104,8 +104,9 @@ class EtaInversion(DiffusionInversion):
             # The reference re-seeds its generator with the same seed on every edit (eta_inversion.py:276), so the
             # candidate table is a constant of (seed, steps, K): keep the device copy instead of redrawing 8M normals
             # on the host and uploading 32 MB per edit.  Read-only by contract.
+            torch.cuda.current_stream(self.model.device).synchronize()  # upload complete before other streams see it
             if len(_NOISE_TABLES) >= 4:
-                _NOISE_TABLES.pop(next(iter(_NOISE_TABLES)))
+                _NOISE_TABLES.pop(next(iter(_NOISE_TABLES)), None)
             _NOISE_TABLES[key] = table
         return table
 

@@ -105,6 +105,14 @@ class EtaiPipeline:
         self.device = torch.device(device)
 
 
+def clone_pipeline(pipe: "EtaiPipeline", usd: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0) -> "EtaiPipeline":
+    """A second pipeline on the same device for ``batching.run_pipelined``: its own UNet engine (activation arena, CUDA
+    graphs, stream; same weights), sharing the read-only VAE / text encoder / tokenizer of ``pipe``."""
+    usd = usd if usd is not None else synthetic.random_state_dict(synthetic.unet_param_spec(), seed)
+    unet = UNetEngine(usd, dtype=pipe.unet.dtype, device=pipe.device, max_batch=pipe.unet.max_batch)
+    return EtaiPipeline(unet, pipe.vae, pipe.text_encoder, pipe.tokenizer, sd_scheduler(), pipe.device)
+
+
 def sd_scheduler() -> DDIMScheduler:
     """modules/models/__init__.py:134 plus steps_offset=1 from the SD-1.x pipeline config."""
     return DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,

@@ -44,12 +44,21 @@ def gather_results(local: Dict[int, Any], n: int, world: int) -> List[Any]:
     return [merged[i] for i in range(n)]
 
 
-def run_sweep(n: int, rank: int, world: int, cobatch: int, run_group: Callable[[List[int]], List[Any]]) -> List[Any]:
-    """Drive a sweep: `run_group(indices)` edits one lock-step group and returns one record per index."""
+def run_sweep(n: int, rank: int, world: int, cobatch: int, run_group: Callable[[List[int]], List[Any]],
+              window: int = 1, run_groups: Callable[[List[List[int]]], List[List[Any]]] = None) -> List[Any]:
+    """Drive a sweep: `run_group(indices)` edits one lock-step group and returns one record per index.
+    With `run_groups` (and `window` > 1) the rank's groups are handed over `window` at a time, so that several groups
+    can be in flight on the GPU (batching.run_pipelined); records come back per group, in order."""
     local: Dict[int, Any] = {}
-    for grp in group_indices(shard_indices(n, rank, world), cobatch):
-        recs = run_group(grp)
-        if len(recs) != len(grp):
-            raise RuntimeError("run_group must return one record per sample")
-        local.update(dict(zip(grp, recs)))
+    groups = list(group_indices(shard_indices(n, rank, world), cobatch))
+    step = max(1, window) if run_groups is not None else 1
+    for w0 in range(0, len(groups), step):
+        chunk = groups[w0:w0 + step]
+        recs_per_group = run_groups(chunk) if run_groups is not None else [run_group(chunk[0])]
+        if len(recs_per_group) != len(chunk):
+            raise RuntimeError("run_groups must return one record list per group")
+        for grp, recs in zip(chunk, recs_per_group):
+            if len(recs) != len(grp):
+                raise RuntimeError("run_group must return one record per sample")
+            local.update(dict(zip(grp, recs)))
     return gather_results(local, n, world)

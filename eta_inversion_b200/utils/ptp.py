@@ -22,7 +22,7 @@ from typing import Dict, List, Optional, Sequence, Tuple, Union
 import torch
 import torch.nn.functional as nnf
 
-from ..engine import AttnControl
+from ..engine import AttnControl, h2d
 from . import ptp_utils, seq_aligner
 
 MAX_NUM_WORDS = 77
@@ -46,7 +46,7 @@ class LocalBlend:
             for word in words_:
                 ind = ptp_utils.get_word_inds(prompt, word, self.model.tokenizer)
                 alpha_layers[i, ind] = 1
-        self.alpha_layers = alpha_layers.to(self.model.device)  # [prompts, 77]
+        self.alpha_layers = h2d(alpha_layers, self.model.device)  # [prompts, 77]
         self.start_blend = int(start_blend * self.model.scheduler.num_inference_steps)
         self.counter = 0
         self.th = th
@@ -167,7 +167,7 @@ class AttentionControlEdit(AttentionStore):
         self.batch_size = len(prompts)
         alpha_host = ptp_utils.get_time_words_attention_alpha(prompts, num_steps, cross_replace_steps, model.tokenizer)
         self._alpha_active = [bool(a.any()) for a in alpha_host]  # host copy: skip the edit when a step's alpha is all 0
-        self.cross_replace_alpha = alpha_host.to(model.device)
+        self.cross_replace_alpha = h2d(alpha_host, model.device)
         if type(self_replace_steps) is float:
             self_replace_steps = 0, self_replace_steps
         self.num_self_replace = int(num_steps * self_replace_steps[0]), int(num_steps * self_replace_steps[1])
@@ -211,7 +211,7 @@ class AttentionReplace(AttentionControlEdit):
                  local_blend: Optional[LocalBlend] = None, attn_replace_thres=None) -> None:
         super().__init__(model, prompts, num_steps, cross_replace_steps, self_replace_steps, local_blend,
                          attn_replace_thres=attn_replace_thres)
-        self.mapper = seq_aligner.get_replacement_mapper(prompts, model.tokenizer).to(model.device)
+        self.mapper = h2d(seq_aligner.get_replacement_mapper(prompts, model.tokenizer), model.device)
         self._mapper = self.mapper.float()
 
 
@@ -220,7 +220,7 @@ class AttentionRefine(AttentionControlEdit):
                  local_blend: Optional[LocalBlend] = None) -> None:
         super().__init__(model, prompts, num_steps, cross_replace_steps, self_replace_steps, local_blend)
         self.mapper, alphas = seq_aligner.get_refinement_mapper(prompts, model.tokenizer)
-        self.mapper, alphas = self.mapper.to(model.device), alphas.to(model.device)
+        self.mapper, alphas = h2d(self.mapper, model.device), h2d(alphas, model.device)
         self.alphas = alphas.reshape(alphas.shape[0], 1, 1, alphas.shape[1])
         # gather base[..., mapper[n]] as a one-hot 77x77 matrix (index -1 wraps like torch indexing; its alpha is 0)
         onehot = torch.zeros((1, MAX_NUM_WORDS, MAX_NUM_WORDS), device=model.device)
@@ -233,7 +233,7 @@ class AttentionReweight(AttentionControlEdit):
     def __init__(self, model, prompts, num_steps: int, cross_replace_steps, self_replace_steps, equalizer: torch.Tensor,
                  local_blend: Optional[LocalBlend] = None, controller: Optional[AttentionControlEdit] = None) -> None:
         super().__init__(model, prompts, num_steps, cross_replace_steps, self_replace_steps, local_blend)
-        self.equalizer = equalizer.to(model.device)
+        self.equalizer = h2d(equalizer, model.device)
         self.prev_controller = controller
         if controller is not None:
             self._mapper, self._blend_a, _ = controller.edit_tables()

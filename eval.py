@@ -22,7 +22,8 @@ import yaml
 
 import eta_inversion_b200 as etai
 from eta_inversion_b200 import synthetic as syn
-from eta_inversion_b200.batching import run_lockstep
+from eta_inversion_b200.batching import run_lockstep, run_pipelined
+from eta_inversion_b200.models import clone_pipeline
 from eta_inversion_b200.sweep import run_sweep
 
 PIE_DEFAULT_PTP = dict(is_replace_controller=False, cross_replace_steps={"default_": .4}, self_replace_steps=0.6)  # pie_bench_data.py:59-70
@@ -46,7 +47,7 @@ def combos(cfg):
         yield i, dict(zip(keys, vals))
 
 
-def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int) -> None:
+def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int, pipes: int = 1) -> None:
     import cv2
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -56,6 +57,7 @@ def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int) -> None:
     spec = yaml.safe_load(Path(cfg).read_text())
     root = Path("result") / Path(cfg).stem
     pipe, (_, postproc) = etai.load_diffusion_model("synthetic-sd15", f"cuda:{local}", variant=prec, max_batch=4 * cobatch)
+    all_pipes = [pipe] + [clone_pipeline(pipe) for _ in range(max(1, pipes) - 1)]  # groups in flight per GPU
     for ci, combo in combos(spec):
         data = combo["data"] if isinstance(combo["data"], dict) else {"type": combo["data"]}
         n = min(int(data.get("n", 700)), limit) if limit else int(data.get("n", 700))
@@ -67,22 +69,33 @@ def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int) -> None:
             inv = etai.load_inverter(model=p, **method)
             return etai.load_editor(inverter=inv, **edit_method)
 
+        def run_groups(groups):
+            """`pipes` lock-step groups in flight: one group's setup / VAE / host copies hide behind another's UNet."""
+            samples = [[synthetic_pie_sample(i) for i in idx] for idx in groups]
+            todo = [[s for s in ss if override or not (out_dir / f"{s['name']}.png").exists()] for ss in samples]
+            jobs = [[dict(image=s["image"].cuda(), source_prompt=s["source_prompt"], target_prompt=s["target_prompt"],
+                          cfg={**s["edit_cfg"]} if edit_method["type"] == "ptp" else None,
+                          inv_cfg=dict(edit_word_idx=s["edit_word_idx"])) for s in td] for td in todo]
+            live = [g for g, j in enumerate(jobs) if j]
+            if len(all_pipes) > 1 and len(live) > 1:
+                res = dict(zip(live, run_pipelined(all_pipes, [jobs[g] for g in live], make_editor)))
+            else:
+                res = {g: run_lockstep(pipe, jobs[g], make_editor) for g in live}
+            out = []
+            for g, ss in enumerate(samples):
+                recs = {}
+                for s, r in zip(todo[g], res.get(g, [])):
+                    if r is None:
+                        recs[s["name"]] = {"name": s["name"], "status": "unsupported"}
+                        continue
+                    cv2.imwrite(str(out_dir / f"{s['name']}.png"), cv2.cvtColor(postproc(r["image"]), cv2.COLOR_RGB2BGR))
+                    recs[s["name"]] = {"name": s["name"], "status": "done", "latent_mean": float(r["latent"].mean())}
+                out.append([recs.get(s["name"], {"name": s["name"], "status": "skipped"}) for s in ss])
+            return out
+
         def run_group(idx):
-            samples = [synthetic_pie_sample(i) for i in idx]
-            todo = [s for s in samples if override or not (out_dir / f"{s['name']}.png").exists()]
-            jobs = [dict(image=s["image"].cuda(), source_prompt=s["source_prompt"], target_prompt=s["target_prompt"],
-                         cfg={**s["edit_cfg"]} if edit_method["type"] == "ptp" else None,
-                         inv_cfg=dict(edit_word_idx=s["edit_word_idx"])) for s in todo]
-            results = run_lockstep(pipe, jobs, make_editor) if jobs else []
-            recs = {}
-            for s, r in zip(todo, results):
-                if r is None:
-                    recs[s["name"]] = {"name": s["name"], "status": "unsupported"}
-                    continue
-                cv2.imwrite(str(out_dir / f"{s['name']}.png"), cv2.cvtColor(postproc(r["image"]), cv2.COLOR_RGB2BGR))
-                recs[s["name"]] = {"name": s["name"], "status": "done", "latent_mean": float(r["latent"].mean())}
-            return [recs.get(s["name"], {"name": s["name"], "status": "skipped"}) for s in samples]
-        records = run_sweep(n, rank, world, cobatch, run_group)
+            return run_groups([idx])[0]
+        records = run_sweep(n, rank, world, cobatch, run_group, window=4 * len(all_pipes), run_groups=run_groups)
         if rank == 0:
             (out_dir.parent / "records.yaml").write_text(yaml.safe_dump(records))
             print(f"combo {ci}: {sum(r['status'] == 'done' for r in records)} edited, "
@@ -98,4 +111,5 @@ if __name__ == "__main__":
     ap.add_argument("--override", action="store_true", help="Override old results.")
     ap.add_argument("--prec", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--limit", type=int, default=0, help="Only the first N samples (smoke runs).")
+    ap.add_argument("--pipes", type=int, default=2, help="Lock-step groups in flight per GPU (each on its own engine).")
     main(**vars(ap.parse_args()))

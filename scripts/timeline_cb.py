@@ -51,3 +51,26 @@ print(f"engine kernels {etai_t:.1f} ms, other {tot - etai_t:.1f} ms")
 rows = sorted(ka, key=lambda e: -e.self_device_time_total)
 for e in rows[:45]:
     print(f"{e.self_device_time_total / 1e3:9.2f} ms  n={e.count:6d}  {e.key[:110]}")
+
+# ---- host pacing: CPU-side interval between consecutive forward launches (no GPU sync in the loop, so this is pure
+# host time per lock-step round; it must stay below the GPU forward time for the GPU never to starve) ----
+from eta_inversion_b200 import batching  # noqa: E402
+
+stamps = []
+_orig_run = batching.LockstepGroup._run
+
+
+def _run(self):
+    stamps.append(time.perf_counter())
+    return _orig_run(self)
+
+
+batching.LockstepGroup._run = _run
+t0 = time.perf_counter(); step(); wall = 1e3 * (time.perf_counter() - t0)
+import numpy as np  # noqa: E402
+d = np.diff(np.array(stamps)) * 1e3
+n = len(d)
+print(f"wall {wall:.1f} ms, {len(stamps)} forwards; host interval between launches: inversion half mean {d[:n // 2].mean():.2f} ms "
+      f"(p90 {np.percentile(d[:n // 2], 90):.2f}), edit half mean {d[n // 2:].mean():.2f} ms (p90 {np.percentile(d[n // 2:], 90):.2f}), "
+      f"first launch at {1e3 * (stamps[0] - t0):.1f} ms, last launch at {1e3 * (stamps[-1] - t0):.1f} ms")
+print("intervals (ms):", np.round(d[:12], 2), "...", np.round(d[n // 2 - 2:n // 2 + 10], 2), "...", np.round(d[-6:], 2))
