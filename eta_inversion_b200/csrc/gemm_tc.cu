@@ -131,7 +131,7 @@ struct Smem {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int EPI_BYTES = 8 * 2 * 32 * 64;  // 8 epilogue warps x 2 buffers x [32 rows x 32 cols] 16-bit
-    static constexpr int STAGES = (168 * 1024) / STAGE_BYTES > 6 ? 6 : (168 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = (190 * 1024) / STAGE_BYTES > 6 ? 6 : (190 * 1024) / STAGE_BYTES;
     static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
     static constexpr int BAR_OFF = EPI_OFF + EPI_BYTES;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + slack for manual 1024-B alignment
