@@ -290,6 +290,14 @@ def main():
     breakdown = {k: {"ms_per_edit": round(v["ms"], 2), "launches": v["launches"],
                      "tflops": round(2.0 * macs[k] * rows / 1e12 / (v["ms"] / 1e3), 1) if k in macs and v["ms"] > 0 else None}
                  for k, v in prof.items()}
+    # DRAM traffic of the dominant kernel: one `ncu --set full` capture per round, kept under profiles/ (per launch)
+    traffic_bytes, traffic_note = None, None
+    tpath = Path(__file__).resolve().parent / "profiles" / "r01_ncu_conv_traffic.json"
+    if dom == "conv3x3" and tpath.exists():
+        tj = json.loads(tpath.read_text())
+        traffic_bytes = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        traffic_note = (f"{tj['launch']}: {traffic_bytes / 1e6:.1f} MB DRAM traffic vs {tj['algorithmic_bytes'] / 1e6:.1f} MB "
+                        f"algorithmic (in + weights + out) in {tj['duration_us']} us under ncu; {tj['note']}")
     value = world * K * CB * G / (ms_total / 1e3)
     line = {
         "metric": "edits/sec etainv+PtP SD1.5 512^2 50-step", "value": value, "unit": "edits/s", "n_gpus": world, "steps": K,
@@ -308,7 +316,7 @@ def main():
         "roofline": {"bound": "tensor", "kernel": {"conv3x3": "gemm_tc_k<conv>", "gemm": "gemm_tc_k<dense>",
                                                      "self_attn": "attention"}[dom],
                      "achieved": round(achieved, 1), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(achieved / tf_peak, 4),
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": traffic_bytes, "traffic_note": traffic_note, "peak_source": peak_src,
                      "note": f"{dom}: {dom_tflop:.1f} TFLOP per edit ({rows} UNet rows) / {prof[dom]['ms']:.1f} ms of CUDA-event time",
                      "unet_tflops_all_kernels": round(2.0 * macs["total"] * rows / 1e12 / (unet_ms / 1e3), 1),
                      "breakdown": breakdown},
