@@ -284,9 +284,16 @@ def main():
     macs = flops.unet_macs_per_row()
     rows = ROWS_PER_EDIT(args.inv_steps)
     unet_ms = sum(v["ms"] for v in prof.values())
-    dom = max(("conv3x3", "gemm", "self_attn"), key=lambda k: prof[k]["ms"])
-    dom_tflop = 2.0 * macs[dom] * rows / 1e12
-    achieved = dom_tflop / (prof[dom]["ms"] / 1e3)
+    # conv3x3 and the dense projections are ONE kernel (gemm_tc_k<T,BN,CONV>: the conv instantiation only differs in how the
+    # TMA producer addresses the A operand), so they are accounted together as the dominant kernel
+    gemm_ms = prof["conv3x3"]["ms"] + prof["gemm"]["ms"]
+    if gemm_ms >= prof["self_attn"]["ms"]:
+        dom, dom_ms, dom_tflop = "conv3x3", gemm_ms, 2.0 * (macs["conv3x3"] + macs["gemm"]) * rows / 1e12
+        dom_name = "gemm_tc_k (implicit-GEMM conv3x3 + dense instantiations)"
+    else:
+        dom, dom_ms, dom_tflop = "self_attn", prof["self_attn"]["ms"], 2.0 * macs["self_attn"] * rows / 1e12
+        dom_name = "attn_d40_k / attn_tc2_k / attn_tc_k"
+    achieved = dom_tflop / (dom_ms / 1e3)
     breakdown = {k: {"ms_per_edit": round(v["ms"], 2), "launches": v["launches"],
                      "tflops": round(2.0 * macs[k] * rows / 1e12 / (v["ms"] / 1e3), 1) if k in macs and v["ms"] > 0 else None}
                  for k, v in prof.items()}
@@ -313,11 +320,10 @@ def main():
         "clocks": clocks.summary(),
         "e2e": {"value": world * K * CB * G / e2e_s, "unit": "edits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": {"conv3x3": "gemm_tc_k<conv>", "gemm": "gemm_tc_k<dense>",
-                                                     "self_attn": "attention"}[dom],
+        "roofline": {"bound": "tensor", "kernel": dom_name,
                      "achieved": round(achieved, 1), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(achieved / tf_peak, 4),
                      "traffic": traffic_bytes, "traffic_note": traffic_note, "peak_source": peak_src,
-                     "note": f"{dom}: {dom_tflop:.1f} TFLOP per edit ({rows} UNet rows) / {prof[dom]['ms']:.1f} ms of CUDA-event time",
+                     "note": f"{dom_tflop:.1f} TFLOP per edit ({rows} UNet rows) / {dom_ms:.1f} ms of CUDA-event time per edit",
                      "unet_tflops_all_kernels": round(2.0 * macs["total"] * rows / 1e12 / (unet_ms / 1e3), 1),
                      "breakdown": breakdown},
     }
