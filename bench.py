@@ -178,6 +178,8 @@ def main():
     pipe, (preproc, postproc) = etai.load_diffusion_model("synthetic-sd15", f"cuda:{local}", variant=args.variant,
                                                           max_batch=4 * CB)
     pipes = [pipe] + [clone_pipeline(pipe) for _ in range(G - 1)]
+    for p_ in pipes:
+        p_.cache_text_embeddings = False  # the reference's timed region contains the 4 CLIP passes of every edit
 
     def make_editor(p):
         inv = etai.load_inverter(type="etainv", model=p, scheduler="ddim", num_inference_steps=args.inv_steps,

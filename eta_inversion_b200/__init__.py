@@ -7,6 +7,7 @@ registries with identical names and constructor keywords, ``load_inverter`` / ``
 """
 from __future__ import annotations
 
+from functools import partial
 from typing import Callable, List
 
 from .editing.editor import Editor
@@ -17,9 +18,11 @@ from .editing.ptp_editor import PromptToPromptEditor
 from .editing.simple_editor import SimpleEditor
 from .inversion.diffusion_inversion import DiffusionInversion
 from .inversion.direct_inversion import DirectInversion
+from .inversion.ddpm_inversion import DDPMInversion
 from .inversion.eta_inversion import EtaInversion
 from .inversion.negative_prompt_inversion import NegativePromptInversion
 from .inversion.proximal_negative_prompt_inversion import ProximalNegativePromptInversion
+from .inversion.regularized_diffusion_inversion import RegularizedDiffusionInversion
 from .models import StablePostProc, StablePreprocess, load_diffusion_model  # noqa: F401
 
 __version__ = "0.1.0"
@@ -39,9 +42,9 @@ _inverters = {
     "nti": _out_of_scope("nti", "needs the UNet dgrad path"),
     "proxnpi": ProximalNegativePromptInversion,
     "edict": _out_of_scope("edict", "coupled-latent scheduler is outside the hot-path scope"),
-    "ddpminv": _out_of_scope("ddpminv", "DDPM inverse scheduler is outside the hot-path scope"),
-    "cyclediff": _out_of_scope("cyclediff", "DDPM inverse scheduler is outside the hot-path scope"),
-    "regdiffinv": _out_of_scope("regdiffinv", "needs autograd through the UNet"),
+    "ddpminv": DDPMInversion,
+    "cyclediff": partial(DDPMInversion, markovian_forward=True),
+    "regdiffinv": RegularizedDiffusionInversion,
 }
 
 _editors = {

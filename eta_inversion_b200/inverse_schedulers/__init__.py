@@ -1,1 +1,2 @@
-from .schedulers import DDIMScheduler, DDIMInverseScheduler, DiffusionInverseScheduler, FrozenConfig  # noqa: F401
+from .schedulers import (DDIMScheduler, DDIMInverseScheduler, DDPMInverseScheduler, DiffusionInverseScheduler,  # noqa: F401
+                         FrozenConfig)

@@ -176,3 +176,75 @@ class DDIMInverseScheduler(DiffusionInverseScheduler):
     def step(self, noise_pred, t, latent):
         t_from, t_to = self._endpoints(t)
         return DDIMInverseScheduler.Output(self.ddim_step(latent, noise_pred, t_from, t_to))
+
+
+class DDPMInverseScheduler(DiffusionInverseScheduler):
+    """Inverse "DDPM" scheduler of DDPM inversion / CycleDiffusion (ddpm_inverse_scheduler.py:9-203): noises z0 into a
+    trajectory x_T..x_1 (independently from z0, or as a Markov chain when ``markovian_forward``) and recovers, for every
+    step, the noise map z_t that makes the eta = 1 DDIM step land exactly on the sampled x_{t-1}."""
+
+    Output = namedtuple("DDPMInverseSchedulerOutput", ("prev_sample", "variance_noise"))
+
+    def __init__(self, scheduler: DDIMScheduler, inv_steps: str = "sameshift", eta: int = 1, markovian_forward: bool = False):
+        self.scheduler, self.inv_steps, self.markovian_forward = scheduler, inv_steps, markovian_forward
+        self.etas, self.t_to_idx = None, None
+
+    @staticmethod
+    def from_scheduler(scheduler: DDIMScheduler, inv_steps: str = "sameshift", markovian_forward: bool = False, **kwargs):
+        return DDPMInverseScheduler(DDIMScheduler.from_config({**scheduler.config, **kwargs}), inv_steps=inv_steps,
+                                    markovian_forward=markovian_forward)
+
+    def set_timesteps(self, num_inference_steps: int) -> None:
+        self.scheduler.set_timesteps(num_inference_steps)
+        self.t_to_idx = {int(v): k for k, v in enumerate(self.scheduler.timesteps)}
+        self.etas = [1.0] * num_inference_steps
+
+    @property
+    def timesteps(self):
+        return list(reversed(self.scheduler.timesteps))
+
+    def _prev(self, t: int) -> int:
+        return int(t) - self.scheduler.config.num_train_timesteps // self.scheduler.num_inference_steps
+
+    def get_variance(self, timestep) -> float:
+        return _f(self.scheduler._get_variance(int(timestep), self._prev(timestep)))
+
+    def sample_latents(self, latent: torch.Tensor, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """[steps + 1, 4, h, w]: x_t for every inference timestep (index = position in the DESCENDING timestep list) and
+        z0 last.  One N(0,1) draw per timestep, ascending in t, from ``generator`` (ddpm_inverse_scheduler.py:104-128)."""
+        n = len(self.timesteps)
+        gdev = generator.device if generator is not None else latent.device
+        xts = torch.zeros((n,) + tuple(latent.shape[1:]), dtype=latent.dtype, device=latent.device)
+        cur = latent
+        for t in reversed(self.scheduler.timesteps):
+            t = int(t)
+            r = torch.randn(latent.shape, device=gdev, generator=generator).to(latent.device, latent.dtype)
+            a_t = self.scheduler.alpha(t)
+            if not self.markovian_forward:
+                x = latent * (a_t ** 0.5) + r * ((1 - a_t) ** 0.5)
+            else:
+                tp = self._prev(t)
+                ratio = a_t / (self.scheduler.alpha(tp) if tp >= 0 else 1.0)
+                cur = cur * (ratio ** 0.5) + r * ((1 - ratio) ** 0.5)
+                x = cur
+            xts[self.t_to_idx[t]] = x[0]
+        return torch.cat([xts, latent], dim=0)
+
+    def get_sampled_latent_by_t(self, xts: torch.Tensor, t) -> torch.Tensor:
+        return xts[self.t_to_idx[int(t)]][None]
+
+    def get_eta_by_t(self, t) -> float:
+        return self.etas[self.t_to_idx[int(t)]]
+
+    def step(self, noise_pred: torch.Tensor, t, latent: torch.Tensor, xts: torch.Tensor):
+        t = int(t)
+        idx = self.t_to_idx[t]
+        eta = self.etas[idx]
+        a_t = self.scheduler.alpha(t)
+        a_p = self.scheduler.alpha(self._prev(t))  # alpha(-k) = final_alpha_cumprod
+        var = self.get_variance(t)
+        xt, xtm1 = xts[idx][None], xts[idx + 1][None]
+        x0 = (xt - (1 - a_t) ** 0.5 * noise_pred) / a_t ** 0.5
+        mu = a_p ** 0.5 * x0 + (1 - a_p - eta * var) ** 0.5 * noise_pred
+        z = (xtm1 - mu) / (eta * var ** 0.5)
+        return DDPMInverseScheduler.Output(mu + (eta * var ** 0.5) * z, z)

@@ -114,6 +114,8 @@ class DiffusionInversion:
         return (latent * 0.18215).float()  # latent trajectory is kept in fp32
 
     def _embed(self, text: str) -> torch.Tensor:
+        if not getattr(self.model, "cache_text_embeddings", True):  # bench.py: every edit pays for its own CLIP passes
+            return self._embed_uncached(text)
         cache = self.model.__dict__.setdefault("_text_embedding_cache", {})  # weights are frozen: same text, same embedding
         if text in cache:
             return cache[text]

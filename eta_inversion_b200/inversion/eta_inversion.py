@@ -24,9 +24,6 @@ from ..editing.ptp_editor import PromptToPromptControllerAttentionStore
 from .diffusion_inversion import DiffusionInversion
 
 
-_NOISE_TABLES: Dict[Any, torch.Tensor] = {}  # (seed, steps, K, hw, device) -> [steps,K,1,4,hw,hw] candidate noise
-
-
 class ControllerAttentionStorePerStep(PromptToPromptControllerAttentionStore):
     def __init__(self, model, prompt, res, from_where, callback) -> None:
         super().__init__(model, max_size=res)
@@ -62,7 +59,11 @@ class EtaInversion(DiffusionInversion):
                  guidance_scale_bwd: Optional[float] = None, guidance_scale_fwd: Optional[float] = None,
                  verbose: bool = False, eta=(0.0, 0.4), noise_sample_count: int = 10, seed: int = 0,
                  eta_start: Optional[float] = None, eta_end: Optional[float] = None, use_mask=True,
-                 mask_mode_cfg=None) -> None:
+                 mask_mode_cfg=None, noise_device: Optional[str] = None) -> None:
+        """Same keywords as the reference (eta_inversion.py:26-37) plus ``noise_device``: where the seeded generator of the
+        candidate noise lives.  None = the model's device, which is what the reference does
+        (``torch.Generator(device=self.model.device)``, eta_inversion.py:276); "cpu" = a host generator, whose stream does
+        not depend on the device (the golden fixtures were written by the reference running on the CPU)."""
         if use_mask:
             dft = dict(attn_from_where=["up", "down"], attn_res=16, mask_dirinv=None, mask_eta="fwd_mean", pow=None,
                        target_dirinv=None, thres=0.2)
@@ -81,34 +82,26 @@ class EtaInversion(DiffusionInversion):
         self.attn_maps_forward: Dict[Any, Any] = {}
         self.noise_sample_count = noise_sample_count
         self.seed = seed if seed >= 0 else None
-        self.noise_provider = None  # optional callable(step_index) -> [K,1,4,64,64]; default = seeded CPU stream
+        self.noise_device = noise_device
+        self.noise_provider = None  # optional callable(step_index) -> [K,1,4,64,64]; default = seeded generator
 
     # ---- noise -----------------------------------------------------------------------------------
     def sample_variance_noise(self, n: int, generator: Optional[torch.Generator] = None) -> torch.Tensor:
         hw = self.unet.latent_hw
-        return torch.randn((n, 1, 4, hw, hw), generator=generator).to(self.model.device)
+        dev = generator.device if generator is not None else self.model.device
+        return torch.randn((n, 1, 4, hw, hw), generator=generator, device=dev).to(self.model.device)
 
     def _noise_for_loop(self, steps: int) -> torch.Tensor:
         if self.noise_provider is not None:
             return torch.stack([self.noise_provider(i) for i in range(steps)]).to(self.model.device, torch.float32)
         hw = self.unet.latent_hw
-        key = (self.seed, steps, self.noise_sample_count, hw, str(self.model.device))
-        if self.seed is not None and key in _NOISE_TABLES:
-            return _NOISE_TABLES[key]
-        g = torch.Generator()
+        dev = torch.device(self.noise_device) if self.noise_device is not None else self.model.device
+        g = torch.Generator(device=dev)
         if self.seed is not None:
             g.manual_seed(self.seed)
         # one draw for the whole loop == the reference's per-step draws from one generator (numel multiple of 16)
-        table = torch.randn((steps, self.noise_sample_count, 1, 4, hw, hw), generator=g).to(self.model.device)
-        if self.seed is not None:
-            # The reference re-seeds its generator with the same seed on every edit (eta_inversion.py:276), so the
-            # candidate table is a constant of (seed, steps, K): keep the device copy instead of redrawing 8M normals
-            # on the host and uploading 32 MB per edit.  Read-only by contract.
-            torch.cuda.current_stream(self.model.device).synchronize()  # upload complete before other streams see it
-            if len(_NOISE_TABLES) >= 4:
-                _NOISE_TABLES.pop(next(iter(_NOISE_TABLES)), None)
-            _NOISE_TABLES[key] = table
-        return table
+        table = torch.randn((steps, self.noise_sample_count, 1, 4, hw, hw), generator=g, device=dev)
+        return table.to(self.model.device)
 
     # ---- masks -----------------------------------------------------------------------------------
     def get_mask(self, key, mask, t, edit_word_idx):

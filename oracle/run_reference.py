@@ -47,6 +47,18 @@ SCENARIOS = {
     "npi_simple_3": (dict(type="npi", scheduler="ddim", num_inference_steps=3), "simple", {}, None, None),
     "diffinv_pnp_5": (dict(type="diffinv", scheduler="ddim", num_inference_steps=5), "pnp", {}, None, None),
     "proxnpi_simple_3": (dict(type="proxnpi", scheduler="ddim", num_inference_steps=3), "simple", {}, None, None),
+    # cross combinations of the registries (test/test_edit.py:66-108 sweeps inverters x editors)
+    "npi_ptp_replace_3": (dict(type="npi", scheduler="ddim", num_inference_steps=3), "ptp", {}, PTP_REPLACE, None),
+    "dirinv_masactrl_4": (dict(type="dirinv", scheduler="ddim", num_inference_steps=4), "masactrl", {}, None, None),
+    "etainv_pnp_4": (dict(type="etainv", scheduler="ddim", num_inference_steps=4, eta=(0.0, 0.4)), "pnp", {}, None,
+                     dict(edit_word_idx=(1, 1))),
+    "etainv_simple_3": (dict(type="etainv", scheduler="ddim", num_inference_steps=3, eta=0.3), "simple", {}, None,
+                        dict(edit_word_idx=(1, 1))),
+    # DDPM inversion / CycleDiffusion: sampled forward trajectory + recovered noise maps, 36 % of the steps skipped
+    "ddpminv_simple_6": (dict(type="ddpminv", num_inference_steps=6), "simple", {}, None, None),
+    "cyclediff_ptp_replace_5": (dict(type="cyclediff", num_inference_steps=5), "ptp", {}, PTP_REPLACE, None),
+    # DDIM inversion with pix2pix-zero's noise regularisation (auto-correlation + KL gradient steps on the noise)
+    "regdiffinv_simple_3": (dict(type="regdiffinv", scheduler="ddim", num_inference_steps=3), "simple", {}, None, None),
 }
 
 

@@ -25,6 +25,8 @@ def run_scenario(pipe, name):
     import eta_inversion_b200 as etai
     from eta_inversion_b200 import synthetic as syn
     inv_kw, ed_type, ed_kw, cfg, inv_cfg = SCENARIOS[name]
+    if inv_kw["type"] in ("etainv", "ddpminv", "cyclediff"):
+        inv_kw = {**inv_kw, "noise_device": "cpu"}  # the goldens were written by the reference running on the CPU
     inverter = etai.load_inverter(model=pipe, **inv_kw)
     editor = etai.load_editor(inverter=inverter, type=ed_type, **ed_kw)
     rec = {"bwd": [], "inv": None}
