@@ -19,6 +19,7 @@ from .editing.simple_editor import SimpleEditor
 from .inversion.diffusion_inversion import DiffusionInversion
 from .inversion.direct_inversion import DirectInversion
 from .inversion.ddpm_inversion import DDPMInversion
+from .inversion.edict_inversion import EdictInversion
 from .inversion.eta_inversion import EtaInversion
 from .inversion.negative_prompt_inversion import NegativePromptInversion
 from .inversion.proximal_negative_prompt_inversion import ProximalNegativePromptInversion
@@ -41,7 +42,7 @@ _inverters = {
     "etainv": EtaInversion,
     "nti": _out_of_scope("nti", "needs the UNet dgrad path"),
     "proxnpi": ProximalNegativePromptInversion,
-    "edict": _out_of_scope("edict", "coupled-latent scheduler is outside the hot-path scope"),
+    "edict": EdictInversion,
     "ddpminv": DDPMInversion,
     "cyclediff": partial(DDPMInversion, markovian_forward=True),
     "regdiffinv": RegularizedDiffusionInversion,

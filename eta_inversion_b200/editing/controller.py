@@ -38,3 +38,37 @@ class ControllerBase:
 class ControllerEmpty(ControllerBase):
     def copy(self, **kwargs) -> "ControllerEmpty":
         return self
+
+
+class EdictController(ControllerBase):
+    """One copy of the wrapped controller per latent of EDICT's coupled pair (modules/editing/controller.py:71-110); the
+    copy that belongs to the latent being updated receives the step callbacks and supplies the attention control."""
+
+    def __init__(self, controller: ControllerBase) -> None:
+        self.controllers = [controller.copy(latent_idx=i) for i in range(2)]
+        self.cur_latent_idx = None
+
+    def begin(self) -> None:
+        self.cur_latent_idx = None
+        for c in self.controllers:
+            c.begin()
+
+    def end(self) -> None:
+        for c in self.controllers:
+            c.end()
+
+    def begin_step(self, latent_idx: int, latent_base: torch.Tensor, latent_model_input: torch.Tensor) -> None:
+        self.cur_latent_idx = latent_idx
+        self.controllers[latent_idx].begin_step(latent_base)
+
+    def end_step(self, latent: torch.Tensor, **kwargs) -> torch.Tensor:
+        return self.controllers[self.cur_latent_idx].end_step(latent=latent, **kwargs)
+
+    def attn_control(self, unet, batch_rows: int):
+        # the inversion pass runs without step callbacks (no controller is current): plain attention, like the reference,
+        # whose hooks only see the forwards of the latent selected in begin_step
+        return None if self.cur_latent_idx is None else self.controllers[self.cur_latent_idx].attn_control(unet, batch_rows)
+
+    def after_forward(self) -> None:
+        if self.cur_latent_idx is not None:
+            self.controllers[self.cur_latent_idx].after_forward()

@@ -59,6 +59,9 @@ SCENARIOS = {
     "cyclediff_ptp_replace_5": (dict(type="cyclediff", num_inference_steps=5), "ptp", {}, PTP_REPLACE, None),
     # DDIM inversion with pix2pix-zero's noise regularisation (auto-correlation + KL gradient steps on the noise)
     "regdiffinv_simple_3": (dict(type="regdiffinv", scheduler="ddim", num_inference_steps=3), "simple", {}, None, None),
+    # EDICT: coupled latent pair, two UNet calls per step, exact inversion
+    "edict_simple_4": (dict(type="edict", scheduler="ddim", num_inference_steps=4), "simple", {}, None, None),
+    "edict_ptp_replace_3": (dict(type="edict", scheduler="ddim", num_inference_steps=3), "ptp", {}, PTP_REPLACE, None),
 }
 
 
@@ -74,6 +77,11 @@ def build_model():
     pipe = sd15.build_pipeline(syn.random_state_dict(syn.unet_param_spec(), 0),
                                syn.random_state_dict(syn.vae_param_spec(), 1), seed=0)
     return pipe, syn
+
+
+def as_tensor(x) -> torch.Tensor:
+    """EDICT carries a PAIR of coupled latents (a list): stored as one tensor with the pair stacked on the batch axis."""
+    return torch.cat([as_tensor(v) for v in x]) if isinstance(x, (list, tuple)) else x
 
 
 def pool8(img: torch.Tensor) -> np.ndarray:
@@ -105,8 +113,9 @@ def run_scenario(name, pipe, syn):
 
     def psb(*a, **k):
         new_latent, eps = orig_psb(*a, **k)
-        rec["bwd_latents"].append(new_latent.detach().clone().numpy())
-        rec["bwd_eps"].append(eps.detach().clone().numpy())
+        rec["bwd_latents"].append(as_tensor(new_latent).detach().clone().numpy())
+        if eps is not None:
+            rec["bwd_eps"].append(eps.detach().clone().numpy())
         return new_latent, eps
     inverter.predict_step_backward = psb
     if hasattr(inverter, "get_eta_variance_noise"):
@@ -136,10 +145,10 @@ def run_scenario(name, pipe, syn):
         res = editor.edit(image, SRC, TGT, cfg=None if cfg is None else {**cfg}, inv_cfg=inv_cfg)
     dt = time.perf_counter() - t0
     out = dict(
-        inv_latents=np.stack([l.numpy() for l in inv_box["res"]["latents"]]),
-        inv_eps=np.stack([e.numpy() for e in inv_box["res"]["noise_preds"]]),
-        bwd_latents=np.stack(rec["bwd_latents"]), bwd_eps=np.stack(rec["bwd_eps"]),
-        latent=res["latent"].numpy(), latent_inv=res["latent_inv"].numpy(),
+        inv_latents=np.stack([as_tensor(l).numpy() for l in inv_box["res"]["latents"]]),
+        inv_eps=np.stack([e.numpy() for e in inv_box["res"]["noise_preds"] if e is not None] or [np.zeros(0)]),
+        bwd_latents=np.stack(rec["bwd_latents"]), bwd_eps=np.stack(rec["bwd_eps"] or [np.zeros(0)]),
+        latent=as_tensor(res["latent"]).numpy(), latent_inv=as_tensor(res["latent_inv"]).numpy(),
         image_pool8=pool8(res["image"]), image_inv_pool8=pool8(res["image_inv"]),
         image_mean=np.array([res["image"].mean().item(), res["image_inv"].mean().item()]),
         seconds=np.array(dt),

@@ -508,7 +508,8 @@ class AutoencoderKL(nn.Module):
 # --------------------------------------------------------------------------------------
 # DDIM scheduler (diffusers 0.21.1 semantics)
 # --------------------------------------------------------------------------------------
-DDIMSchedulerOutput = namedtuple("DDIMSchedulerOutput", ("prev_sample", "pred_original_sample"))
+# diffusers: a dataclass whose pred_original_sample is optional (the reference's EDICT scheduler passes one field)
+DDIMSchedulerOutput = namedtuple("DDIMSchedulerOutput", ("prev_sample", "pred_original_sample"), defaults=(None,))
 
 
 class DDIMScheduler:

@@ -63,6 +63,6 @@ def test_registry_surface_matches_reference():
         "diffinv", "nti", "npi", "proxnpi", "edict", "ddpminv", "cyclediff", "dirinv", "etainv", "regdiffinv"}
     assert set(etai.get_edit_methods()) == {"simple", "ptp", "masactrl", "pnp", "pix2pix_zero", "invedit"}
     with pytest.raises(NotImplementedError):
-        etai.load_inverter(type="edict", model=None)
+        etai.load_editor(type="pix2pix_zero", inverter=None)
     with pytest.raises(NotImplementedError):
         etai.load_inverter(type="nti", model=None)

@@ -21,6 +21,11 @@ def pipe_fp32():
     return pipe
 
 
+def _t(x):
+    """EDICT carries a pair of coupled latents (a list): compared as one tensor, the pair stacked on the batch axis."""
+    return torch.cat([_t(v) for v in x]) if isinstance(x, (list, tuple)) else x
+
+
 def run_scenario(pipe, name):
     import eta_inversion_b200 as etai
     from eta_inversion_b200 import synthetic as syn
@@ -34,7 +39,7 @@ def run_scenario(pipe, name):
 
     def psb(*a, **k):
         out = orig_psb(*a, **k)
-        rec["bwd"].append(out[0].detach().clone())
+        rec["bwd"].append(_t(out[0]).detach().clone())
         return out
 
     def inv(*a, **k):
@@ -50,7 +55,7 @@ def run_scenario(pipe, name):
 def test_fp32_trajectory_matches_reference(pipe_fp32, name):
     gold = np.load(GOLDEN / f"{name}.npz")
     res, rec, inverter = run_scenario(pipe_fp32, name)
-    inv = torch.stack([l.cpu() for l in rec["inv"]["latents"]])
+    inv = torch.stack([_t(l).cpu() for l in rec["inv"]["latents"]])
     err_inv = (inv - torch.from_numpy(gold["inv_latents"])).abs().amax(dim=(1, 2, 3, 4))
     bwd = torch.stack([l.cpu() for l in rec["bwd"]])
     err_bwd = (bwd - torch.from_numpy(gold["bwd_latents"])).abs().amax(dim=(1, 2, 3, 4))
@@ -61,8 +66,8 @@ def test_fp32_trajectory_matches_reference(pipe_fp32, name):
         assert (m - torch.from_numpy(gold["fwd_mean_map"])).abs().max() < 1e-3
     assert err_inv.max() < TOL_LATENT
     assert err_bwd.max() < TOL_LATENT
-    assert (res["latent"].cpu() - torch.from_numpy(gold["latent"])).abs().max() < TOL_LATENT
-    assert (res["latent_inv"].cpu() - torch.from_numpy(gold["latent_inv"])).abs().max() < TOL_LATENT
+    assert (_t(res["latent"]).cpu() - torch.from_numpy(gold["latent"])).abs().max() < TOL_LATENT
+    assert (_t(res["latent_inv"]).cpu() - torch.from_numpy(gold["latent_inv"])).abs().max() < TOL_LATENT
     pooled = torch.nn.functional.avg_pool2d(res["image"].float().cpu(), 8)
     assert (pooled - torch.from_numpy(gold["image_pool8"])).abs().max() < 5e-3
 
