@@ -19,6 +19,15 @@ def _worker(rank, world, port, out):
     assert [r["sample"] for r in res] == list(range(23))
     assert all(r["rank"] == r["sample"] % world for r in res)
     assert all(len(c) <= 4 for c in calls) and sum(len(c) for c in calls) == len(range(rank, 23, world))
+    # windowed form (several lock-step groups handed over at once, as eval.py does for batching.run_pipelined)
+    windows = []
+
+    def run_groups(groups):
+        windows.append([list(g) for g in groups])
+        return [run_group(g) for g in groups]
+    res2 = run_sweep(23, rank, world, cobatch=4, run_group=run_group, window=2, run_groups=run_groups)
+    assert res2 == res
+    assert all(len(w) <= 2 for w in windows) and sum(len(g) for w in windows for g in w) == len(range(rank, 23, world))
     out[rank] = [r["checksum"] for r in res]
     dist.destroy_process_group()
 
