@@ -582,13 +582,14 @@ constexpr int AT3_THREADS = 384;  // warpgroup 0: warp 0 TMA, warps 1-2 UMMA iss
 // issues the UMMAs of both query tiles (head-of-line blocking: tile 0's PV waits behind tile 1's P).  This version removes
 // every wait from the steady state:
 //   * 64-key tiles, S double-buffered per query tile (S_{j+2} is issued as soon as P_j is published);
-//   * P double-buffered in shared memory (P_j may be written while PV_{j-1} still reads P_{j-1}; PV_{j-2} is known to
-//     be complete because S_j, issued after it by the same thread, is);
+//   * P goes straight from the softmax registers to TMEM (tcgen05.st) and feeds PV as the TMEM A operand of a TS-mode
+//     UMMA: no shared-memory round trip, no 4 KB A-tile read per k-step; double-buffered (P_j may be written while
+//     PV_{j-1} still reads P_{j-1}; PV_{j-2} is complete because S_j, issued after it by the same thread, is);
 //   * O accumulates in TMEM across tiles and is rescaled lazily: the running maximum is only raised when it grew by
 //     more than 2^8 (P stays <= 256, exact in fp16/bf16 relative precision; the row sum shares the stale maximum
 //     through the "ones" column, so the result is the same softmax), so the O read-modify-write is off the common path;
 //   * one UMMA-issuing thread per query tile with descriptors reduced to one add per k-step.
-// TMEM: S[g][b] 64 columns at g*128 + b*64, O[g] at 256 + g*64.
+// TMEM: S[g][b] 64 columns at g*128 + b*64, O[g] at 256 + g*64, P[g][b] 32 columns at 384 + g*64 + b*32.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
@@ -619,9 +620,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 // UMMA with descriptors given as (low word, shared high word); ACC is compile-time so no predicate has to be computed
 template <bool ACC>
 __device__ __forceinline__ void umma_lohi(uint32_t d, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc) {
@@ -637,6 +635,21 @@ __device__ __forceinline__ void umma_lohi(uint32_t d, uint32_t alo, uint32_t blo
             ::"r"(d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc) : "memory");
 }
 
+// TS-mode UMMA: A operand in TMEM (lane = row, 32-bit column = two consecutive K elements), B from shared memory
+template <bool ACC>
+__device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint32_t blo, uint32_t hi, uint32_t idesc) {
+    if constexpr (ACC)
+        asm volatile(
+            "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\tmov.b64 db, {%2, %3};\n\t"
+            "setp.eq.u32 p, %4, %4;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+            ::"r"(d), "r"(a_tmem), "r"(blo), "r"(hi), "r"(idesc) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .b64 db;\n\t.reg .pred p;\n\tmov.b64 db, {%2, %3};\n\t"
+            "setp.ne.u32 p, %4, %4;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+            ::"r"(d), "r"(a_tmem), "r"(blo), "r"(hi), "r"(idesc) : "memory");
+}
+
 template <typename T>
 __global__ void __launch_bounds__(AT3_THREADS, 1)
 attn_d40_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -645,8 +658,7 @@ attn_d40_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
     constexpr int Q_BYTES = ATOM_BYTES;               // [128 q][64]
     constexpr int KT_BYTES = BK4 * 128;                // one K or V tile: [64 keys][128 B]
     constexpr int KV_BYTES = 2 * KT_BYTES;
-    constexpr int KV_OFF = 2 * Q_BYTES, P_OFF = KV_OFF + STAGES * KV_BYTES;   // P[g][b]: [128 q][64 keys] = one atom
-    constexpr int BAR_OFF = P_OFF + 4 * ATOM_BYTES;
+    constexpr int KV_OFF = 2 * Q_BYTES, BAR_OFF = KV_OFF + STAGES * KV_BYTES;
     constexpr float RESCALE_LOG2 = 8.f;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -701,7 +713,6 @@ attn_d40_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
             const uint32_t lo_k = 1u << 16;                                        // K-major: LBO unused (1)
             const uint32_t lo_mn = (uint32_t)(KT_BYTES >> 4) << 16;                // MN-major V: single 64-wide N atom
             const uint32_t q_lo = lo_k | ((smem_u32(smem + g * Q_BYTES) & 0x3FFFF) >> 4);
-            const uint32_t p_lo = lo_k | ((smem_u32(smem + P_OFF + g * 2 * ATOM_BYTES) & 0x3FFFF) >> 4);
             const uint32_t kv_lo = (smem_u32(smem + KV_OFF) & 0x3FFFF) >> 4;
             const uint32_t tS = tmem_base + (uint32_t)g * 128, tO = tmem_base + 256 + (uint32_t)g * 64;
             auto issue_s = [&](int j) {
@@ -721,13 +732,14 @@ attn_d40_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
                 const int s = j % STAGES;
                 mbar_wait(&p_full[g * 2 + (j & 1)], (j >> 1) & 1);
                 tc_fence_after();
-                const uint32_t a_lo = p_lo + (uint32_t)(j & 1) * (ATOM_BYTES >> 4);
                 const uint32_t v_lo = lo_mn | (kv_lo + (uint32_t)s * (KV_BYTES >> 4) + (KT_BYTES >> 4));
-                if (j == 0) umma_lohi<false>(tO, a_lo, v_lo, hi, idesc_o);
-                else umma_lohi<true>(tO, a_lo, v_lo, hi, idesc_o);
-                umma_lohi<true>(tO, a_lo + 2, v_lo + 128, hi, idesc_o);   // 16 keys: +32 B in P's row, +16 rows of V
-                umma_lohi<true>(tO, a_lo + 4, v_lo + 256, hi, idesc_o);
-                umma_lohi<true>(tO, a_lo + 6, v_lo + 384, hi, idesc_o);
+                // P_j lives in TMEM (A operand of a TS-mode UMMA: no shared-memory read of the 128 x 16 A tile per k-step)
+                const uint32_t tP = tmem_base + 384 + (uint32_t)g * 64 + (uint32_t)(j & 1) * 32;  // 16 keys = 8 columns
+                if (j == 0) umma_ts<false>(tO, tP, v_lo, hi, idesc_o);
+                else umma_ts<true>(tO, tP, v_lo, hi, idesc_o);
+                umma_ts<true>(tO, tP + 8, v_lo + 128, hi, idesc_o);   // +16 key rows of V
+                umma_ts<true>(tO, tP + 16, v_lo + 256, hi, idesc_o);
+                umma_ts<true>(tO, tP + 24, v_lo + 384, hi, idesc_o);
                 umma_commit(&kv_empty[s]);  // count 2: both issuers are done with K_j / V_j
                 umma_commit(&o_full[g]);
                 if (j == ntiles - 1) umma_commit(&o_done[g]);
@@ -741,7 +753,6 @@ attn_d40_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
         const int r = quarter * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
         const uint32_t o_addr = tmem_base + 256 + (uint32_t)g * 64 + lane_addr;
-        const uint32_t p_row = smem_u32(smem + P_OFF + g * 2 * ATOM_BYTES + r * 128);
         const uint32_t ones_addr = smem_u32(smem + KV_OFF + KT_BYTES + r * 128 + (((D >> 3) ^ (r & 7)) * 16) + (D & 7) * 2);
         const uint16_t one = std::is_same<T, __half>::value ? (uint16_t)0x3C00 : (uint16_t)0x3F80;
         float m_run = -INFINITY;
@@ -797,21 +808,22 @@ attn_d40_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
             }
             const float mb = m_run * c;
             // P_j = 2^(s*c - m*c) -> 16-bit, swizzled A-operand tile, buffer j & 1
-            const uint32_t p_dst = p_row + (uint32_t)(j & 1) * ATOM_BYTES;
+            uint32_t pr[32];  // the row's 64 probabilities, packed pairs in key order
 #pragma unroll
             for (int blk = 0; blk < 8; ++blk) {
-                uint32_t pk[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float e0 = ex2_approx(fmaf(__uint_as_float(sv[blk * 8 + 2 * e]), c, -mb));
                     const float e1 = ex2_approx(fmaf(__uint_as_float(sv[blk * 8 + 2 * e + 1]), c, -mb));
                     if constexpr (std::is_same<T, __half>::value)
-                        asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(pk[e]) : "f"(e0), "f"(e1));
+                        asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(pr[blk * 4 + e]) : "f"(e0), "f"(e1));
                     else
-                        asm("cvt.rn.bf16x2.f32 %0, %2, %1;" : "=r"(pk[e]) : "f"(e0), "f"(e1));
+                        asm("cvt.rn.bf16x2.f32 %0, %2, %1;" : "=r"(pr[blk * 4 + e]) : "f"(e0), "f"(e1));
                 }
-                sts128(p_dst + (uint32_t)((blk ^ (r & 7)) * 16), pk[0], pk[1], pk[2], pk[3]);
             }
+            // lane = query row, 32-bit column = key pair: exactly the A-operand layout of a TS-mode UMMA
+            tmem_st32(tmem_base + 384 + (uint32_t)g * 64 + (uint32_t)(j & 1) * 32 + lane_addr, pr);
+            tmem_wait_st();
             // "ones" column D of this stage's V tile (row = key r): O[:, D] accumulates sum_j P[:, j].  Both query tiles
             // write the same value, so neither issuer depends on the other tile's warpgroup.
             if (r < BK4)
@@ -847,7 +859,7 @@ attn_d40_k(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUte
 
 template <typename T>
 void launch_attn_d40(const CUtensorMap& q, const CUtensorMap& k, const CUtensorMap& v, const AtParams& p, dim3 grid, cudaStream_t s) {
-    constexpr int SMEM = 2 * ATOM_BYTES + 4 * 2 * 64 * 128 + 4 * ATOM_BYTES + 256 + 1024;
+    constexpr int SMEM = 2 * ATOM_BYTES + 4 * 2 * 64 * 128 + 256 + 1024;  // Q tiles + 4 K/V stages + barriers
     static bool configured = false;
     if (!configured) {
         CUDA_CHECK(cudaFuncSetAttribute(attn_d40_k<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
