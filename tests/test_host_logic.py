@@ -131,3 +131,41 @@ def test_sharding_covers_every_sample_once():
         gather_results({0: "a"}, 2, 1)
     with pytest.raises(ValueError):
         shard_indices(4, 2, 2)
+
+
+def test_ddpm_and_edict_inverse_schedulers_match_reference():
+    """DDPMInverseScheduler (sampled trajectory, recovered noise maps, variance) and the EDICT scheduler pair (integer and
+    fractional timestep spacing) against the reference's own classes (oracle/make_scheduler_goldens.py)."""
+    import numpy as np
+    from eta_inversion_b200.inverse_schedulers import DDIMScheduler, DDPMInverseScheduler
+    from eta_inversion_b200.inversion.edict_inversion import EdictScheduler, EdictSchedulerInverse
+    from eta_inversion_b200.models import sd_scheduler
+    from pathlib import Path
+    gold = np.load(Path(__file__).parent / "golden" / "schedulers.npz")
+    z0, eps = torch.from_numpy(gold["z0"]), torch.from_numpy(gold["eps"])
+    cfg = sd_scheduler().config
+    for steps in (6, 3):
+        for markov in (False, True):
+            base = DDIMScheduler.from_config(cfg)
+            base.set_timesteps(steps)
+            inv = DDPMInverseScheduler.from_scheduler(base, markovian_forward=markov)
+            inv.set_timesteps(steps)
+            xts = inv.sample_latents(z0, generator=torch.Generator().manual_seed(5))
+            key = f"ddpm_s{steps}_m{int(markov)}"
+            assert np.abs(xts.numpy() - gold[key + "_xts"]).max() < 2e-6
+            for i, t in enumerate(inv.timesteps):
+                r = inv.step(eps[i % 6], t, inv.get_sampled_latent_by_t(xts, t), xts)
+                scale = max(1.0, float(np.abs(gold[key + "_z"][i]).max()))
+                assert np.abs(r.variance_noise.numpy() - gold[key + "_z"][i]).max() < 2e-5 * scale
+                assert np.abs(r.prev_sample.numpy() - gold[key + "_x"][i]).max() < 2e-5
+                assert abs(inv.get_variance(int(t)) - gold[key + "_var"][i]) < 1e-7
+        base = DDIMScheduler.from_config(cfg)
+        base.set_timesteps(steps)
+        bwd, fwd = EdictScheduler(base), EdictSchedulerInverse(base)
+        x = z0.clone()
+        for i, t in enumerate(fwd.timesteps):
+            x = fwd.step(eps[i % 6], t, x).prev_sample
+            assert np.abs(x.numpy() - gold[f"edict_s{steps}_fwd"][i]).max() < 2e-5 * max(1.0, float(x.abs().max()))
+        for i, t in enumerate(bwd.timesteps):
+            x = bwd.step(eps[(steps - 1 - i) % 6], t, x).prev_sample
+            assert np.abs(x.numpy() - gold[f"edict_s{steps}_bwd"][i]).max() < 2e-5 * max(1.0, float(x.abs().max()))
