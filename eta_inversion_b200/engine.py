@@ -8,6 +8,7 @@ Call shape kept from the reference:  ``unet(sample, t, encoder_hidden_states=ctx
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
@@ -19,6 +20,12 @@ from ._lib import (CTRL_CROSS_EDIT, CTRL_CROSS_STORE, CTRL_SELF_REMAP, MATH_AUTO
 
 SD15_CHANNELS = (320, 640, 1280, 1280)
 LAUNCHES = [0]  # kernels launched through the op-level entry points below (the UNet handle counts its own)
+_LAUNCHES_LOCK = threading.Lock()  # lanes of lock-step / pipelined groups call the ops from several threads
+
+
+def _count_launches(n: int) -> None:
+    with _LAUNCHES_LOCK:
+        LAUNCHES[0] += n
 
 
 def _require_cuda(t: torch.Tensor, name: str) -> None:
@@ -317,7 +324,7 @@ def cfg_ddim_step(eps, x, a_from: float, a_to: float, guidance: Optional[float] 
     check(_lib.load().etai_cfg_ddim_step(ptr(eps), n, int(has_cfg), float(guidance or 0.0), ptr(x), ptr(out), ptr(eps_out),
                                          float(a_from), float(a_to), float(eta), float(variance), ptr(eta_map),
                                          ptr(noise_cand), ptr(losses), K, ptr(pin_src), E, stream_ptr()))
-    LAUNCHES[0] += 1
+    _count_launches(1)
     return (out, eps_out) if want_eps else out
 
 
@@ -331,5 +338,5 @@ def eta_noise_losses(eps, x, x_prev_inv, a_from: float, a_to: float, guidance: O
     check(_lib.load().etai_eta_noise_losses(ptr(eps), n, int(guidance is not None), float(guidance or 0.0), ptr(x),
                                             ptr(x_prev_inv), float(a_from), float(a_to), float(eta), float(variance),
                                             ptr(noise_cand), K, E, ptr(losses), ptr(best), stream_ptr()))
-    LAUNCHES[0] += 2
+    _count_launches(2)
     return losses, best
