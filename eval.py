@@ -56,8 +56,11 @@ def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int, pipes: i
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     spec = yaml.safe_load(Path(cfg).read_text())
     root = Path("result") / Path(cfg).stem
-    pipe, (_, postproc) = etai.load_diffusion_model("synthetic-sd15", f"cuda:{local}", variant=prec, max_batch=4 * cobatch)
-    all_pipes = [pipe] + [clone_pipeline(pipe) for _ in range(max(1, pipes) - 1)]  # groups in flight per GPU
+    usd = syn.random_state_dict(syn.unet_param_spec(), 0)  # generated once, shared by the engine instances
+    pipe, (_, postproc) = etai.load_diffusion_model("synthetic-sd15", f"cuda:{local}", variant=prec, max_batch=4 * cobatch,
+                                                    unet_state_dict=usd)
+    all_pipes = [pipe] + [clone_pipeline(pipe, usd) for _ in range(max(1, pipes) - 1)]  # groups in flight per GPU
+    del usd
     for ci, combo in combos(spec):
         data = combo["data"] if isinstance(combo["data"], dict) else {"type": combo["data"]}
         n = min(int(data.get("n", 700)), limit) if limit else int(data.get("n", 700))
