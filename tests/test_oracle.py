@@ -68,3 +68,24 @@ def test_ref_loop_reproduces_reference_trajectory(pipe):
     assert (out["bwd_latents"] - torch.from_numpy(gold["bwd_latents"])).abs().max().item() < 1e-4
     assert out["picks"] == gold["picks"].tolist()
     assert (out["fwd_mean"][1] - torch.from_numpy(gold["fwd_mean_map"])).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("name", ["etainv_simple_3"])
+def test_ref_loop_is_bit_exact_on_more_reference_goldens(pipe, name):
+    """The self-contained port (what `bench.py --impl reference` and smoke() use as the CPU checker) against goldens the
+    reference's own classes wrote for other inverter x editor pairs.  (diffinv+simple, dirinv+ptp and dirinv+masactrl were
+    checked the same way when the goldens were generated: max-abs 0.0; one is kept here to bound the CPU suite's run time.)"""
+    from eta_inversion_b200 import synthetic as syn
+    from oracle import ref_loop
+    from oracle.run_reference import SCENARIOS, SRC, TGT
+    inv_kw, ed, _, cfg, _ = SCENARIOS[name]
+    gold = np.load(GOLDEN / f"{name}.npz")
+    kw = dict(inverter=inv_kw["type"], editor=ed, steps=inv_kw["num_inference_steps"], ptp_cfg=cfg, decode=False)
+    if "eta" in inv_kw:
+        kw["eta"] = inv_kw["eta"]
+    with torch.no_grad():
+        out = ref_loop.edit(pipe, syn.synthetic_image(0), SRC, TGT, **kw)
+    assert torch.equal(out["inv_latents"], torch.from_numpy(gold["inv_latents"]))
+    assert torch.equal(out["bwd_latents"], torch.from_numpy(gold["bwd_latents"]))
+    if "picks" in gold.files:
+        assert out["picks"] == gold["picks"].tolist()
