@@ -80,7 +80,10 @@ def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int, pipes: i
                           cfg={**s["edit_cfg"]} if edit_method["type"] == "ptp" else None,
                           inv_cfg=dict(edit_word_idx=s["edit_word_idx"])) for s in td] for td in todo]
             live = [g for g, j in enumerate(jobs) if j]
-            if len(all_pipes) > 1 and len(live) > 1:
+            if edit_method["type"] == "pnp":  # feature injection is not mergeable across lanes: one edit at a time
+                with torch.no_grad():
+                    res = {g: [make_editor(pipe).edit(**j) for j in jobs[g]] for g in live}
+            elif len(all_pipes) > 1 and len(live) > 1:
                 res = dict(zip(live, run_pipelined(all_pipes, [jobs[g] for g in live], make_editor)))
             else:
                 res = {g: run_lockstep(pipe, jobs[g], make_editor) for g in live}
