@@ -95,7 +95,8 @@ def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int, pipes: i
                         recs[s["name"]] = {"name": s["name"], "status": "unsupported"}
                         continue
                     cv2.imwrite(str(out_dir / f"{s['name']}.png"), cv2.cvtColor(postproc(r["image"]), cv2.COLOR_RGB2BGR))
-                    recs[s["name"]] = {"name": s["name"], "status": "done", "latent_mean": float(r["latent"].mean())}
+                    lat = r["latent"][0] if isinstance(r["latent"], (list, tuple)) else r["latent"]  # EDICT: coupled pair
+                    recs[s["name"]] = {"name": s["name"], "status": "done", "latent_mean": float(lat.mean())}
                 out.append([recs.get(s["name"], {"name": s["name"], "status": "skipped"}) for s in ss])
             return out
 
