@@ -178,7 +178,7 @@ def main():
     usd = syn.random_state_dict(syn.unet_param_spec(), 0)  # generated once, shared by the G engine instances
     pipe, (preproc, postproc) = etai.load_diffusion_model("synthetic-sd15", f"cuda:{local}", variant=args.variant,
                                                           max_batch=4 * CB, unet_state_dict=usd)
-    pipes = [pipe] + [clone_pipeline(pipe, usd) for _ in range(G - 1)]
+    pipes = [pipe] + [clone_pipeline(pipe) for _ in range(G - 1)]
     del usd
     for p_ in pipes:
         p_.cache_text_embeddings = False  # the reference's timed region contains the 4 CLIP passes of every edit

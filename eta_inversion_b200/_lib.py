@@ -56,6 +56,7 @@ SYMBOLS = {
     "etai_last_error": (C.c_char_p, []),
     "etai_unet_create": (C.c_int, [C.POINTER(_vp), C.POINTER(EtaiUnetCfg), C.POINTER(EtaiTensor), _i32, _i32]),
     "etai_unet_destroy": (C.c_int, [_vp]),
+    "etai_unet_clone": (C.c_int, [C.POINTER(_vp), _vp, _i32]),
     "etai_unet_set_context": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "etai_unet_forward": (C.c_int, [_vp, _vp, _f, _i32, _i32, C.POINTER(EtaiAttnCtrl), _vp, _vp]),
     "etai_unet_device_bytes": (_i64, [_vp]),
@@ -69,6 +70,9 @@ SYMBOLS = {
     "etai_conv3x3": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
     "etai_attention": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f,
                                  C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _i32, _i32, _vp]),
+    "etai_cross_attention": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _f, _i32,
+                                       C.POINTER(_i32), C.POINTER(_i32), _vp, _vp, _vp, _vp, _i32, C.POINTER(_i32), _vp,
+                                       _i32, _i32, _vp, _i64, _vp]),
 }
 
 _lib = None

@@ -34,12 +34,20 @@ class _LaneUNet:
 
 
 class LockstepGroup:
+    """Rendez-vous of the lanes' ``unet(...)`` calls.  The set of LIVE lanes shrinks when a lane finishes (an edit that
+    returns None because it is unsupported -- eta_inversion.py:385-386 of the reference --, or one that simply takes fewer
+    UNet forwards than its peers): the remaining lanes keep walking in lock step with a smaller merged batch instead of
+    waiting for a request that will never come."""
+
     def __init__(self, engine: UNetEngine, lanes: int, timeout_s: float = 600.0) -> None:
         self.engine, self.lanes, self.timeout = engine, lanes, timeout_s
-        self._barrier = threading.Barrier(lanes)
-        self._req: List[Any] = [None] * lanes
-        self._out: List[Any] = [None] * lanes
+        self._cv = threading.Condition()
+        self._live = set(range(lanes))
+        self._req: Dict[int, Any] = {}
+        self._out: Dict[int, Any] = {}
+        self._gen = 0
         self._err: Optional[BaseException] = None
+        self._aborted = False
         self._ctx_key, self._ctx_cat = None, None
         self.forwards = 0
 
@@ -47,28 +55,50 @@ class LockstepGroup:
         return _LaneUNet(self, lane)
 
     def abort(self) -> None:
-        self._barrier.abort()
+        with self._cv:
+            self._aborted = True
+            self._cv.notify_all()
+
+    def lane_done(self, lane: int) -> None:
+        """Lane `lane` will post no more requests; if the others were only waiting for it, their forward runs now."""
+        with self._cv:
+            self._live.discard(lane)
+            if self._live and not self._aborted and len(self._req) == len(self._live):
+                self._run_locked()
 
     # ---- called concurrently by the lane threads ---------------------------------------------------
     def forward(self, lane: int, sample, timestep, ctx, control) -> UNetOutput:
-        self._req[lane] = (sample, timestep, ctx, control)
-        try:
-            if self._barrier.wait(self.timeout) == 0:  # every lane has posted its request; one thread runs the engine
-                try:
-                    self._run()
-                except BaseException as e:  # noqa: BLE001 - re-raised in every lane below
-                    self._err = e
-            self._barrier.wait(self.timeout)
-        except threading.BrokenBarrierError:
-            raise RuntimeError("etai lockstep: a lane left the loop early (edits in one group must take the same "
-                               "number of UNet forwards)") from self._err
-        if self._err is not None:
-            raise RuntimeError(f"etai lockstep: batched forward failed: {self._err}") from self._err
-        return UNetOutput(self._out[lane])
+        with self._cv:
+            if self._aborted:
+                raise RuntimeError("etai lockstep: group aborted (another lane failed)") from self._err
+            self._req[lane] = (sample, timestep, ctx, control)
+            gen = self._gen
+            if len(self._req) == len(self._live):  # every live lane has posted its request: this thread runs the engine
+                self._run_locked()
+            elif not self._cv.wait_for(lambda: self._gen != gen or self._aborted, self.timeout):
+                self._aborted = True
+                self._cv.notify_all()
+                raise RuntimeError(f"etai lockstep: lane {lane} waited {self.timeout:.0f} s for its peers")
+            if self._err is not None:
+                raise RuntimeError(f"etai lockstep: batched forward failed: {self._err}") from self._err
+            if self._aborted:
+                raise RuntimeError("etai lockstep: group aborted (another lane failed)")
+            return UNetOutput(self._out.pop(lane))
 
-    # ---- leader ------------------------------------------------------------------------------------
+    # ---- leader (holds the condition's lock; the other lanes are parked in wait_for) ----------------
+    def _run_locked(self) -> None:
+        try:
+            self._run()
+        except BaseException as e:  # noqa: BLE001 - re-raised in every lane
+            self._err = e
+            self._aborted = True
+        self._req = {}
+        self._gen += 1
+        self._cv.notify_all()
+
     def _run(self) -> None:
-        reqs = self._req
+        order = sorted(self._req)          # live lanes, in lane order: rows of lane order[i] are [i*B, (i+1)*B)
+        reqs = [self._req[l] for l in order]
         B = reqs[0][0].shape[0]
         t0 = float(reqs[0][1])
         for s, t, c, _ in reqs:
@@ -76,7 +106,8 @@ class LockstepGroup:
                 raise RuntimeError("lanes disagree on batch rows / timestep / context rows")
         sample = torch.cat([r[0] for r in reqs])
         old = self._ctx_key  # strong references to the lanes' context tensors + their versions (addresses can be reused)
-        same = old is not None and all(o[0] is r[2] and o[1] == r[2]._version for o, r in zip(old, reqs))
+        same = old is not None and len(old) == len(reqs) and all(o[0] is r[2] and o[1] == r[2]._version
+                                                                 for o, r in zip(old, reqs))
         if not same:  # contexts are constant over a loop: concatenate (and re-project K/V) only on change
             self._ctx_key = [(r[2], r[2]._version) for r in reqs]
             self._ctx_cat = torch.cat([r[2] for r in reqs]).contiguous()
@@ -84,8 +115,8 @@ class LockstepGroup:
         eps = self.engine(sample, t0, encoder_hidden_states=self._ctx_cat, control=ctrl)["sample"]
         for fn in scatter:
             fn()
-        for l in range(self.lanes):
-            self._out[l] = eps[l * B:(l + 1) * B]
+        for i, l in enumerate(order):
+            self._out[l] = eps[i * B:(i + 1) * B]
         self.forwards += 1
 
     def _merge(self, ctrls: Sequence[Optional[AttnControl]], B: int):
@@ -164,6 +195,7 @@ def run_lockstep(pipe, jobs: Sequence[Dict[str, Any]], make_editor: Callable[[An
             torch.cuda.set_device(dev)
             with torch.no_grad(), torch.cuda.stream(stream):  # stream=None is a no-op context
                 results[l] = editors[l].edit(**jobs[l])
+            group.lane_done(l)  # the peers go on without this lane (it may have returned early, e.g. None = unsupported)
         except BaseException as e:  # noqa: BLE001
             errors[l] = e
             group.abort()
@@ -179,8 +211,8 @@ def run_lockstep(pipe, jobs: Sequence[Dict[str, Any]], make_editor: Callable[[An
             th.join()
     finally:
         sys.setswitchinterval(old_interval)
-    for e in errors:
-        if e is not None and not isinstance(e, threading.BrokenBarrierError):
+    for e in errors:  # the root cause first: lanes that were merely aborted report "group aborted"
+        if e is not None and "group aborted" not in str(e):
             raise e
     for e in errors:
         if e is not None:

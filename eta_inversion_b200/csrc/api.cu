@@ -1,4 +1,5 @@
 // C ABI for the scheduler kernels and the individually exported ops (see include/etai.h).
+#include <cstring>
 #include "ops.cuh"
 
 using namespace etai;
@@ -127,6 +128,70 @@ int etai_attention(const void* q, const void* k, const void* v, void* out, int32
         attention_tc(a, (cudaStream_t)stream);
     } else {
         attention_simt(a, (cudaStream_t)stream);
+    }
+    ETAI_API_END
+}
+
+int etai_cross_attention(const void* q, const void* kv, void* out, int32_t B, int32_t N, int32_t L, int32_t heads, int32_t d,
+                         int32_t ldq, int32_t ldkv, int32_t ldo, int32_t koff, int32_t voff, float scale, int32_t n_pairs,
+                         const int32_t* edit_base_row, const int32_t* edit_tgt_row, const float* mapper,
+                         const float* blend_a, const float* equalizer, const float* alpha_step, int32_t n_store_rows,
+                         const int32_t* store_row, float* store_acc, int32_t dtype, int32_t math_mode, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
+    ETAI_API_BEGIN
+    ETAI_CHECK(q && kv && out && B >= 1 && B <= ETAI_MAX_ROWS && N >= 1 && L >= 1 && heads >= 1, ETAI_ERR_ARG,
+               "cross_attention: null/empty argument");
+    ETAI_CHECK(n_pairs >= 0 && n_pairs <= ETAI_MAX_PAIRS && n_store_rows >= 0 && n_store_rows <= ETAI_MAX_ROWS, ETAI_ERR_ARG,
+               "cross_attention: pair / store row count out of range");
+    if (n_pairs > 0)
+        ETAI_CHECK(edit_base_row && edit_tgt_row && mapper && blend_a && equalizer && alpha_step, ETAI_ERR_ARG,
+                   "cross_attention: edit tables missing");
+    if (n_store_rows > 0) ETAI_CHECK(store_row && store_acc, ETAI_ERR_ARG, "cross_attention: store arguments missing");
+    cudaStream_t s = (cudaStream_t)stream;
+    CrossAttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.q = q; a.kv = kv; a.out = out;
+    a.B = B; a.N = N; a.L = L; a.heads = heads; a.d = d;
+    a.ldq = ldq; a.ldkv = ldkv; a.ldo = ldo; a.koff = koff; a.voff = voff; a.scale = scale; a.dtype = dtype;
+    int slot_of[ETAI_MAX_ROWS];
+    bool used[ETAI_MAX_ROWS] = {false};
+    for (int r = 0; r < B; ++r) slot_of[r] = -1;
+    for (int i = 0; i < n_store_rows; ++i) {
+        ETAI_CHECK(store_row[i] >= 0 && store_row[i] < B, ETAI_ERR_ARG, "cross_attention: store row out of range");
+        slot_of[store_row[i]] = i;
+    }
+    if (n_store_rows > 0) a.store = store_acc;
+    int ng = 0;
+    if (n_pairs > 0) {
+        a.mapper = mapper; a.blend_a = blend_a; a.equalizer = equalizer; a.alpha_step = alpha_step;
+        for (int p = 0; p < n_pairs; ++p) {
+            int br = edit_base_row[p], tr = edit_tgt_row[p];
+            ETAI_CHECK(br >= 0 && br < B && tr >= 0 && tr < B && br != tr && !used[br] && !used[tr], ETAI_ERR_ARG,
+                       "cross_attention: bad edit pair");
+            used[br] = used[tr] = true;
+            a.groups[ng++] = CrossGroup{br, tr, p, slot_of[br], slot_of[tr]};
+        }
+    }
+    for (int r = 0; r < B; ++r)
+        if (!used[r]) a.groups[ng++] = CrossGroup{r, -1, 0, slot_of[r], -1};
+    a.n_groups = ng;
+    if (math_mode == ETAI_MATH_AUTO && dtype != ETAI_F32) {
+        // workspace: [16-bit mapper operand][per-head store partials]
+        size_t mb = (cross_attention_tc_mapper_bytes(ETAI_MAX_PAIRS) + 255) & ~size_t(255);
+        size_t sb = n_store_rows > 0 ? (size_t)heads * n_store_rows * N * L * sizeof(float) : 0;
+        ETAI_CHECK(workspace && (size_t)workspace_bytes >= mb + sb, ETAI_ERR_ARG,
+                   "cross_attention: workspace too small (need 327680 + heads*n_store_rows*N*L*4 bytes)");
+        if (n_pairs > 0) {
+            CUDA_CHECK(cudaMemsetAsync(workspace, 0, mb, s));
+            cross_attention_tc_prep_mapper(mapper, workspace, n_pairs, L, dtype, s);
+            a.map16 = workspace;
+        }
+        a.store_part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + mb);
+        ETAI_CHECK(cross_attention_tc_supported(a), ETAI_ERR_UNSUPPORTED,
+                   "cross_attention: shape not supported by the tcgen05 path");
+        cross_attention_tc(a, s);
+    } else {
+        cross_attention(a, s);
     }
     ETAI_API_END
 }

@@ -6,6 +6,7 @@
 //   conv OIHW -> [O][ky][kx][I] (implicit-GEMM K order), to_q/to_k/to_v of attn1 stacked to one [3C,C] GEMM,
 //   all 16 cross-attention to_k/to_v stacked to one [sum 2C, 768] GEMM that runs once per context,
 //   all 22 time_emb_proj stacked to one skinny GEMM, GEGLU rows interleaved (value,gate) for the fused epilogue.
+#include <memory>
 #include <unordered_map>
 #include <vector>
 #include <string>
@@ -31,6 +32,17 @@ struct Tfm {
 
 // fp32 scratch layout of the time-embedding path
 constexpr int TB_SIN = 0, TB_H1 = 4096, TB_ST = 8192, TB_PROJ = 16384;
+
+// Packed device weights, shared (read-only) between a handle and its clones.
+struct WeightStore {
+    std::vector<void*> owned;
+    size_t bytes = 0;
+    int device = 0;
+    ~WeightStore() {
+        cudaSetDevice(device);
+        for (void* p : owned) cudaFree(p);
+    }
+};
 
 struct Arena {
     char* base = nullptr;
@@ -58,7 +70,7 @@ struct etai_unet {
     int dt = ETAI_F32;   // storage dtype
     bool tc = false;     // tcgen05 path enabled
     size_t esz = 4;
-    std::vector<void*> owned;  // device allocations (weights)
+    std::shared_ptr<WeightStore> wstore;  // device allocations of the packed weights (shared with clones)
     size_t weight_bytes = 0;
 
     Conv conv_in, conv_out;
@@ -128,7 +140,8 @@ struct etai_unet {
     void* dmalloc(size_t bytes) {
         void* p = nullptr;
         CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 256));
-        owned.push_back(p);
+        wstore->owned.push_back(p);
+        wstore->bytes += bytes;
         weight_bytes += bytes;
         return p;
     }
@@ -814,6 +827,8 @@ int etai_unet_create(etai_unet** out, const etai_unet_cfg* cfg, const etai_tenso
     try {
         h->cfg = *cfg;
         h->device = device;
+        h->wstore = std::make_shared<WeightStore>();
+        h->wstore->device = device;
         h->dt = cfg->dtype;
         h->esz = dtype_size(cfg->dtype);
         h->tc = cfg->dtype != ETAI_F32 && cfg->math_mode == ETAI_MATH_AUTO;
@@ -831,7 +846,8 @@ int etai_unet_create(etai_unet** out, const etai_unet_cfg* cfg, const etai_tenso
 int etai_unet_destroy(etai_unet* h) {
     if (!h) return ETAI_OK;
     cudaSetDevice(h->device);
-    for (void* p : h->owned) cudaFree(p);
+    if (h->gs) cudaStreamSynchronize(h->gs);
+    h->wstore.reset();  // frees the packed weights when this was the last handle using them
     if (h->arena.base) cudaFree(h->arena.base);
     if (h->kv_cache) cudaFree(h->kv_cache);
     if (h->ctx_buf) cudaFree(h->ctx_buf);
@@ -853,6 +869,39 @@ int etai_unet_destroy(etai_unet* h) {
     if (h->stage) cudaFree(h->stage);
     delete h;
     return ETAI_OK;
+}
+
+int etai_unet_clone(etai_unet** out, const etai_unet* src, int32_t max_batch) {
+    ETAI_API_BEGIN
+    ETAI_CHECK(out && src, ETAI_ERR_ARG, "clone: null argument");
+    ETAI_CHECK(max_batch <= ETAI_MAX_ROWS, ETAI_ERR_ARG, "clone: max_batch in [1,64]");
+    CUDA_CHECK(cudaSetDevice(src->device));
+    etai_unet* h = new etai_unet();
+    try {
+        h->cfg = src->cfg;
+        if (max_batch > 0) h->cfg.max_batch = max_batch;
+        h->device = src->device;
+        h->dt = src->dt; h->tc = src->tc; h->esz = src->esz;
+        h->use_graphs = src->use_graphs;
+        h->wstore = src->wstore;  // shared, read-only
+        h->weight_bytes = 0;      // accounted once, by the handle that loaded them
+        h->conv_in = src->conv_in; h->conv_out = src->conv_out; h->norm_out = src->norm_out;
+        h->time1 = src->time1; h->time2 = src->time2; h->temb_all = src->temb_all; h->kv_all = src->kv_all;
+        for (int i = 0; i < 4; ++i) {
+            h->down_res[i] = src->down_res[i]; h->up_res[i] = src->up_res[i];
+            h->down_tf[i] = src->down_tf[i]; h->up_tf[i] = src->up_tf[i];
+        }
+        for (int i = 0; i < 3; ++i) { h->down_samp[i] = src->down_samp[i]; h->up_samp[i] = src->up_samp[i]; }
+        h->mid_res[0] = src->mid_res[0]; h->mid_res[1] = src->mid_res[1];
+        h->mid_tf = src->mid_tf;
+        h->n_tf = src->n_tf; h->temb_total = src->temb_total; h->kv_total = src->kv_total;
+        h->plan_workspace();
+    } catch (...) {
+        etai_unet_destroy(h);
+        throw;
+    }
+    *out = h;
+    ETAI_API_END
 }
 
 int64_t etai_unet_launch_count(const etai_unet* h) { return h ? h->launches : 0; }

@@ -153,6 +153,19 @@ class UNetEngine:
         self._ctx_key = None
         self._timing = None  # list of (start, end) torch events when forward timing is switched on
 
+    def clone(self, max_batch: Optional[int] = None) -> "UNetEngine":
+        """A second engine on the SAME packed device weights (reference counted in the library) with its own activation
+        arena, CUDA graphs, staging buffers and stream: what ``batching.run_pipelined`` runs its second group on."""
+        other = object.__new__(UNetEngine)
+        other.__dict__.update({k: v for k, v in self.__dict__.items() if k not in ("_h", "_ctx_key", "_timing", "control")})
+        other.max_batch = max_batch or self.max_batch
+        other.control, other._ctx_key, other._timing = None, None, None
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self._lib.etai_unet_clone(C.byref(h), self._h, int(other.max_batch)))
+        other._h = h
+        return other
+
     def close(self):
         if getattr(self, "_h", None):
             self._lib.etai_unet_destroy(self._h)
@@ -258,6 +271,40 @@ def conv3x3(x: torch.Tensor, w_packed: torch.Tensor, bias=None, residual=None, s
     check(_lib.load().etai_conv3x3(ptr(x), ptr(w_packed), ptr(bias), ptr(residual), ptr(out), B, H, Wd, Ci, Co, stride,
                                    dtype_code(x.dtype), math_mode, ptr(ws), 0 if ws is None else ws.numel() * ws.element_size(),
                                    stream_ptr()))
+    return out
+
+
+def cross_attention(q: torch.Tensor, kv: torch.Tensor, heads: int, koff: int, voff: int, scale: Optional[float] = None,
+                    edit_pairs=None, mapper=None, blend_a=None, equalizer=None, alpha_step=None, store_rows=None,
+                    store_acc=None, math_mode: int = MATH_AUTO) -> torch.Tensor:
+    """One control-aware cross-attention layer (include/etai.h, etai_cross_attention).
+    q: [B,N,heads*d]; kv: [B,L,ldkv] with K of head h at column koff+h*d and V at voff+h*d."""
+    _require_cuda(q, "q")
+    _require_cuda(kv, "kv")
+    B, N, Cc = q.shape
+    L, d = kv.shape[1], Cc // heads
+    out = torch.empty((B, N, Cc), dtype=q.dtype, device=q.device)
+    P = 0 if edit_pairs is None else len(edit_pairs)
+    if P:
+        for n, t in (("mapper", mapper), ("blend_a", blend_a), ("equalizer", equalizer), ("alpha_step", alpha_step)):
+            _require_cuda(t, n)
+            if t.dtype != torch.float32 or t.shape[0] != P:
+                raise RuntimeError(f"etai: {n} must be fp32 with leading dim {P}")
+    b = i32_array([p[0] for p in edit_pairs]) if P else None
+    t_ = i32_array([p[1] for p in edit_pairs]) if P else None
+    S = 0 if store_rows is None else len(store_rows)
+    sr = i32_array(store_rows) if S else None
+    if S:
+        _require_cuda(store_acc, "store_acc")
+        if store_acc.dtype != torch.float32 or tuple(store_acc.shape) != (S, N, L):
+            raise RuntimeError(f"etai: store_acc must be fp32 [{S},{N},{L}]")
+    ws = torch.empty((327680 + heads * max(S, 1) * N * L * 4,), dtype=torch.uint8, device=q.device)
+    i32p = C.POINTER(C.c_int32)
+    check(_lib.load().etai_cross_attention(
+        ptr(q), ptr(kv), ptr(out), B, N, L, heads, d, q.stride(1), kv.stride(1), Cc, koff, voff,
+        float(scale if scale is not None else d ** -0.5), P, C.cast(b, i32p) if P else None, C.cast(t_, i32p) if P else None,
+        ptr(mapper), ptr(blend_a), ptr(equalizer), ptr(alpha_step), S, C.cast(sr, i32p) if S else None, ptr(store_acc),
+        dtype_code(q.dtype), math_mode, ptr(ws), ws.numel(), stream_ptr()))
     return out
 
 

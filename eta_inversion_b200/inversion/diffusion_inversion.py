@@ -88,20 +88,29 @@ class DiffusionInversion:
                 scheduler_inv_kwargs["inv_steps"] = kwargs.pop("inv_steps")
         else:
             raise Exception(type(scheduler))
-        if name != "ddim":
-            raise NotImplementedError(f"scheduler '{name}': only 'ddim' is built natively (SURVEY.md section 2: ddpm/dpm "
-                                      "inverse schedulers are out of scope for the hot path)")
-        kwargs = {"clip_sample": False, "set_alpha_to_one": False, **kwargs}
+        if name not in self.get_available_schedulers():
+            raise NotImplementedError(f"scheduler '{name}': the DPM-Solver multistep (inverse) scheduler is not built in this "
+                                      f"engine (diffusion_inversion.py:141-142 of the reference); available: "
+                                      f"{self.get_available_schedulers()}")
+        if name == "ddim":
+            kwargs = {"clip_sample": False, "set_alpha_to_one": False, **kwargs}
         bwd = DDIMScheduler.from_config({**model.scheduler.config, **kwargs})
         bwd.set_timesteps(num_inference_steps)
-        fwd = DDIMInverseScheduler.from_scheduler(bwd, **scheduler_inv_kwargs)
+        if name == "ddpm":  # "simulate ddpm with ddim and eta=1" + the DDPM inverse scheduler (diffusion_inversion.py:141,158-160)
+            from ..inverse_schedulers import DDPMInverseScheduler
+            fwd = DDPMInverseScheduler.from_scheduler(bwd, **scheduler_inv_kwargs)
+        else:
+            fwd = DDIMInverseScheduler.from_scheduler(bwd, **scheduler_inv_kwargs)
         fwd.set_timesteps(num_inference_steps)
         assert fwd.timesteps[0] < fwd.timesteps[1], "wrong timestamp order, not increasing"
         return bwd, bwd, fwd
 
     @staticmethod
     def get_available_schedulers() -> List[str]:
-        return ["ddim", "ddpm", "dpm"]
+        """The reference lists ["ddim", "ddpm", "dpm"] (diffusion_inversion.py:174-176); "dpm" (diffusers' DPM-Solver
+        multistep + the reference's inverse of it) is not built here, so it is not advertised: the CLIs reject it at
+        argument parsing instead of failing inside the constructor."""
+        return ["ddim", "ddpm"]
 
     # ---- VAE / text ------------------------------------------------------------------------------
     def decode(self, latent: torch.Tensor) -> torch.Tensor:

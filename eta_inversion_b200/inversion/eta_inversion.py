@@ -99,9 +99,45 @@ class EtaInversion(DiffusionInversion):
         g = torch.Generator(device=dev)
         if self.seed is not None:
             g.manual_seed(self.seed)
-        # one draw for the whole loop == the reference's per-step draws from one generator (numel multiple of 16)
-        table = torch.randn((steps, self.noise_sample_count, 1, 4, hw, hw), generator=g, device=dev)
+        # One randn per step, all drawn before the loop (still no host<->device sync inside it): exactly the reference's
+        # per-step ``torch.randn((K,1,4,64,64), generator=g)`` stream (eta_inversion.py:156,276,348) on either kind of
+        # generator.  (One big draw would only equal it for a CPU generator; the CUDA Philox element mapping depends on
+        # the tensor size.)
+        table = torch.stack([torch.randn((self.noise_sample_count, 1, 4, hw, hw), generator=g, device=dev)
+                             for _ in range(steps)])
         return table.to(self.model.device)
+
+    # ---- API parity: the reference's noise-selection methods as thin wrappers over the kernels ----------------------
+    def _step_coef(self, t):
+        sch = self.scheduler_bwd
+        ti, pi = int(t), sch.prev_timestep(t)
+        return sch.alpha(ti), sch.alpha(pi), float(sch._get_variance(ti, pi))
+
+    def compute_optimal_variance_noise(self, latent_prev, latent, t, eta: float, noise_pred) -> torch.Tensor:
+        """z* = (x_prev^inv - step(eps, eta, z=0)) / (eta * sqrt(var))  (eta_inversion.py:296-317).  ``noise_pred`` is the
+        CFG-combined prediction, like in the reference."""
+        a_t, a_p, var = self._step_coef(t)
+        x, e = latent.float().contiguous(), noise_pred.float().contiguous()
+        rec = E.cfg_ddim_step(e, x, a_t, a_p, None, float(eta), var)  # no candidates: z = 0
+        return (latent_prev.float() - rec) / (float(eta) * var ** 0.5)
+
+    def get_eta_variance_noise(self, latent_prev, latent, t, noise_pred, generator: Optional[torch.Generator] = None
+                               ) -> Dict[str, Any]:
+        """Best-of-K variance noise for the source row (eta_inversion.py:330-375); same result keys.  The edit loop itself
+        does NOT call this (it keeps the pick on the device inside ``etai_cfg_ddim_step``); this wrapper reads the picked
+        index back, like the reference's ``argmin().item()``."""
+        eta = float(self.etas[int(t)])
+        cand = self.sample_variance_noise(self.noise_sample_count, generator).float()
+        a_t, a_p, var = self._step_coef(t)
+        x, e = latent.float().contiguous(), noise_pred.float().contiguous()
+        prev = latent_prev.float().contiguous()
+        flat = cand.reshape(cand.shape[0], -1).contiguous()
+        losses, best = E.eta_noise_losses(e, x, prev, a_t, a_p, None, eta, var, flat)
+        best_idx = int(best.item())
+        variance_noise = cand[best_idx]
+        rec = E.cfg_ddim_step(e, x, a_t, a_p, None, eta, var, None, flat[best_idx:best_idx + 1].contiguous(), None)
+        return {"eta": eta, "variance_noise": variance_noise, "delta": prev - rec, "latent_prev": latent_prev,
+                "latent_prev_rec": rec, "loss": losses[best_idx]}
 
     # ---- masks -----------------------------------------------------------------------------------
     def get_mask(self, key, mask, t, edit_word_idx):

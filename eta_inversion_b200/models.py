@@ -105,12 +105,14 @@ class EtaiPipeline:
         self.device = torch.device(device)
 
 
-def clone_pipeline(pipe: "EtaiPipeline", usd: Optional[Dict[str, torch.Tensor]] = None, seed: int = 0) -> "EtaiPipeline":
-    """A second pipeline on the same device for ``batching.run_pipelined``: its own UNet engine (activation arena, CUDA
-    graphs, stream; same weights), sharing the read-only VAE / text encoder / tokenizer of ``pipe``."""
-    usd = usd if usd is not None else synthetic.random_state_dict(synthetic.unet_param_spec(), seed)
-    unet = UNetEngine(usd, dtype=pipe.unet.dtype, device=pipe.device, max_batch=pipe.unet.max_batch)
-    return EtaiPipeline(unet, pipe.vae, pipe.text_encoder, pipe.tokenizer, sd_scheduler(), pipe.device)
+def clone_pipeline(pipe: "EtaiPipeline", max_batch: Optional[int] = None) -> "EtaiPipeline":
+    """A second pipeline on the same device for ``batching.run_pipelined``: its own UNet engine handle (activation arena,
+    CUDA graphs, stream) on the SAME packed device weights as ``pipe`` (``etai_unet_clone``: nothing is re-uploaded, both
+    groups stream one copy of the weights), sharing the read-only VAE / text encoder / tokenizer of ``pipe``."""
+    clone = EtaiPipeline(pipe.unet.clone(max_batch), pipe.vae, pipe.text_encoder, pipe.tokenizer, sd_scheduler(), pipe.device)
+    if hasattr(pipe, "cache_text_embeddings"):
+        clone.cache_text_embeddings = pipe.cache_text_embeddings
+    return clone
 
 
 def sd_scheduler() -> DDIMScheduler:
@@ -119,20 +121,33 @@ def sd_scheduler() -> DDIMScheduler:
                          set_alpha_to_one=False, steps_offset=1)
 
 
+REAL_MODEL_NAMES = ("sd14", "CompVis/stable-diffusion-v1-4", "runwayml/stable-diffusion-v1-5")
+
+
 def load_diffusion_model(model: str = "synthetic-sd15", device: str = "cuda", preproc_args: Optional[Dict[str, Any]] = None,
                          variant: Optional[str] = None, max_batch: int = 4, seed: int = 0,
                          unet_state_dict: Optional[Dict[str, torch.Tensor]] = None,
-                         vae_state_dict: Optional[Dict[str, torch.Tensor]] = None, **kwargs
+                         vae_state_dict: Optional[Dict[str, torch.Tensor]] = None,
+                         text_encoder: Optional[torch.nn.Module] = None, tokenizer: Any = None, **kwargs
                          ) -> Tuple[EtaiPipeline, Tuple[StablePreprocess, StablePostProc]]:
-    """Same signature/return shape as the reference loader.  ``model``:
-      * "synthetic-sd15" (default; also accepted: "sd14", "CompVis/stable-diffusion-v1-4"): SD-1.x architecture with
-        seeded random-init weights, because no pretrained checkpoint exists in this environment;
-      * or pass ``unet_state_dict`` / ``vae_state_dict`` (diffusers key names) to run real weights.
+    """Same signature/return shape as the reference loader (modules/models/__init__.py:104-138).  ``model``:
+      * "synthetic-sd15" (default): SD-1.x architecture with seeded random-init UNet / VAE / CLIP text tower and the
+        whitespace tokenizer -- the only thing that can be built on a box without checkpoints or network;
+      * "sd14" / "CompVis/stable-diffusion-v1-4" (the reference's names): a REAL checkpoint, which this loader cannot
+        download; all four parts must be supplied -- ``unet_state_dict`` and ``vae_state_dict`` (diffusers key names),
+        ``text_encoder`` (a ``CLIPTextModel``) and ``tokenizer`` (a ``CLIPTokenizer``) -- otherwise it raises instead of
+        silently editing with random weights.
     ``variant``: "fp32" (SIMT fp32 parity path) | "fp16" | "bf16" (tcgen05 path)."""
+    if model in REAL_MODEL_NAMES:
+        missing = [n for n, v in (("unet_state_dict", unet_state_dict), ("vae_state_dict", vae_state_dict),
+                                  ("text_encoder", text_encoder), ("tokenizer", tokenizer)) if v is None]
+        if missing:
+            raise RuntimeError(f"etai: model '{model}' names a pretrained checkpoint, which cannot be downloaded here; pass "
+                               f"{', '.join(missing)} (or use model='synthetic-sd15' for the random-init architecture)")
+    elif model != "synthetic-sd15":
+        raise Exception(model)
     variant = variant or "fp32"
     dtype = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[variant]
-    if model not in ("synthetic-sd15", "sd14", "CompVis/stable-diffusion-v1-4"):
-        raise Exception(model)
     if not str(device).startswith("cuda"):
         raise RuntimeError("etai: the engine runs on CUDA devices only (no CPU fallback)")
     dev = torch.device(device if ":" in str(device) else f"cuda:{torch.cuda.current_device()}")
@@ -148,6 +163,7 @@ def load_diffusion_model(model: str = "synthetic-sd15", device: str = "cuda", pr
     vae.load_state_dict(vae_state_dict if vae_state_dict is not None
                         else synthetic.random_state_dict(synthetic.vae_param_spec(), seed + 1), strict=True)
     vae = vae.to(dev, dtype).to(memory_format=torch.channels_last)
-    text_encoder = make_text_encoder(seed).to(dev, dtype)  # 16-bit variants run CLIP in 16-bit as the reference does
-    pipe = EtaiPipeline(unet, vae, text_encoder, SyntheticTokenizer(), sd_scheduler(), dev)
+    # 16-bit variants run CLIP in 16-bit as the reference does
+    text_encoder = (text_encoder if text_encoder is not None else make_text_encoder(seed)).to(dev, dtype)
+    pipe = EtaiPipeline(unet, vae, text_encoder, tokenizer if tokenizer is not None else SyntheticTokenizer(), sd_scheduler(), dev)
     return pipe, (StablePreprocess(str(dev), size=512, **(preproc_args or {})), StablePostProc())

@@ -17,6 +17,20 @@ Spec = List[Tuple[str, Tuple[int, ...]]]
 UNET_CHANNELS = (320, 640, 1280, 1280)
 CROSS_DIM = 768
 HEADS = 8
+# Gain on the cross-attention to_q / to_k projections of the synthetic UNet.  Variance-preserving random weights give
+# logits of unit variance whose softmax, once averaged over 5 layers x 8 heads, is spatially flat: every eta mask
+# (eta_inversion.py:196-198, > 0.2) and LocalBlend mask (ptp.py:18-47, > 0.3) would be all-ones and the masked code paths
+# would only ever run in their degenerate form.  With this gain the logits are heavy-tailed enough for the per-word maps
+# to have real spatial structure (tests assert the mask fraction is strictly inside (0.05, 0.95)).
+ATTN2_QK_GAIN = 2.0
+# Gain on the token-embedding table of the synthetic CLIP text tower: with transformers' default init (token and position
+# embeddings both std 0.02) the 77 output embeddings of a prompt are ~0.9 cosine-similar, so every word's attention map is
+# the same map; with the gain the word identity dominates (cosine ~0.25 between different words).
+TOKEN_EMB_GAIN = 32.0
+# Gain on the synthetic VAE's quant_conv (weight and bias): SD's 0.18215 scaling factor exists to give latents ~unit
+# variance, a variance-preserving random encoder gives std ~0.13 after it; then conv_in's bias and the time embedding swamp
+# the image content and every UNet feature map is spatially constant.
+VAE_LATENT_GAIN = 16.0
 
 
 def _resnet(prefix: str, cin: int, cout: int, temb: int | None) -> Spec:
@@ -150,12 +164,18 @@ def random_state_dict(spec: Spec, seed: int = 0, dtype=torch.float32) -> Dict[st
             for d in shape[1:]:
                 fan_in *= d
             t = r * (fan_in ** -0.5)
+            if ".attn2.to_q." in name or ".attn2.to_k." in name:
+                t = t * ATTN2_QK_GAIN
+        if name.startswith("quant_conv."):
+            t = t * VAE_LATENT_GAIN
         out[name] = t.to(dtype)
     return out
 
 
 def synthetic_image(seed: int = 0, size: int = 512) -> torch.Tensor:
-    """Smooth low-frequency image in [-1, 1], shape [1,3,size,size]."""
+    """Synthetic image in [-1, 1], shape [1,3,size,size]: a smooth low-frequency background plus
+    three sharp-edged, flat-coloured ellipses ("objects").  The objects matter: a purely smooth image gives spatially
+    flat attention maps under random-init weights, so the eta mask and the LocalBlend mask would be all-ones."""
     g = torch.Generator().manual_seed(10_000 + seed)
     yy, xx = torch.meshgrid(torch.linspace(0, 1, size), torch.linspace(0, 1, size), indexing="ij")
     img = torch.zeros(3, size, size)
@@ -165,7 +185,13 @@ def synthetic_image(seed: int = 0, size: int = 512) -> torch.Tensor:
             amp = float(torch.rand(1, generator=g)) * 0.5
             img[c] += amp * torch.sin(6.2832 * (fx * xx + fy * yy) + ph)
     img += 0.05 * torch.randn(3, size, size, generator=g)
-    return (img / img.abs().max()).clamp(-1, 1)[None].contiguous()
+    img = 0.5 * img / img.abs().max()
+    for _ in range(3):
+        cx, cy, rx, ry = (torch.rand(4, generator=g) * torch.tensor([0.6, 0.6, 0.15, 0.15]) + torch.tensor([0.2, 0.2, 0.1, 0.1])).tolist()
+        colour = (torch.rand(3, generator=g) * 2 - 1) * 0.9
+        inside = ((xx - cx) / rx) ** 2 + ((yy - cy) / ry) ** 2 < 1.0
+        img = torch.where(inside[None], colour[:, None, None] + 0.1 * img, img)
+    return img.clamp(-1, 1)[None].contiguous()
 
 
 def variance_noise_slabs(steps: int, count: int = 10, seed: int = 0) -> torch.Tensor:
@@ -174,3 +200,17 @@ def variance_noise_slabs(steps: int, count: int = 10, seed: int = 0) -> torch.Te
     GPU engine consume identical numbers (RNG quirk)."""
     g = torch.Generator().manual_seed(seed)
     return torch.randn((steps, count, 1, 4, 64, 64), generator=g)
+
+
+def make_text_encoder(seed: int = 0):
+    """Random-init CLIP ViT-L/14 text tower (transformers ``CLIPTextModel``; there are no pretrained weights on the
+    box).  Shared input definition of the oracle and the engine (modules/models/__init__.py:135 loads the real one)."""
+    from transformers import CLIPTextConfig, CLIPTextModel
+    cfg = CLIPTextConfig(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                         num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu")
+    with torch.random.fork_rng():
+        torch.manual_seed(seed)
+        m = CLIPTextModel(cfg)
+    with torch.no_grad():
+        m.text_model.embeddings.token_embedding.weight.mul_(TOKEN_EMB_GAIN)
+    return m.eval().requires_grad_(False)

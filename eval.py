@@ -5,8 +5,8 @@ per sample, sharded PER IMAGE across the GPUs of one box.
     python eval.py --cfg cfg/eval/synthetic_pie.yaml                       # one GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 eval.py --cfg ...
 
-Compared with the reference's eval.py (:27-183): the YAML grid keys (data / model / method / edit_method / edit_cfg)
-and the result layout result/<cfg>/<nn_combo>/imgs/*.png are kept, finished PNGs are skipped unless --override
+Compared with the reference's eval.py (:27-195): the flags (--cfg --device --no_proc --override --skip_existing_dirs), the
+YAML grid keys (data / model / method / edit_method / edit_cfg) and the result layout result/<cfg>/<nn_combo>/imgs/*.png are kept, finished PNGs are skipped unless --override
 (eval_utils.py:260-263); the unit of parallelism is the sample (rank = index mod world, lock-step groups of --cobatch
 inside a rank) instead of one process per config combination, and only per-sample records are gathered at the end.
 The only dataset on this box is the synthetic PIE-shaped one (`data: [{type: synthetic_pie, n: 700}]`)."""
@@ -47,8 +47,34 @@ def combos(cfg):
         yield i, dict(zip(keys, vals))
 
 
-def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int, pipes: int = 1) -> None:
+def respawn_per_device(devices, argv) -> int:
+    """--device a b c (eval.py:163-175 of the reference starts one consumer per device): one rank per listed device under
+    torch.distributed.run, samples sharded per image across them."""
+    import subprocess
+    import sys
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=",".join(devices))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={len(devices)}", "--master-addr",
+           "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), sys.argv[0]] + argv
+    return subprocess.call(cmd, env=env)
+
+
+def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int, pipes: int = 1, device=None, no_proc: bool = False,
+         skip_existing_dirs: bool = False) -> None:
     import cv2
+    if device and "RANK" not in os.environ:
+        if len(device) > 1 and not no_proc:
+            import sys
+            argv, skip = [], 0
+            for a in sys.argv[1:]:  # drop "--device a b c" from the child command line
+                if a == "--device":
+                    skip = 1
+                    continue
+                if skip and not a.startswith("--"):
+                    continue
+                skip = 0
+                argv.append(a)
+            raise SystemExit(respawn_per_device(device, argv))
+        os.environ["CUDA_VISIBLE_DEVICES"] = device[0]  # --no_proc / one device: this process, first listed device
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
@@ -59,13 +85,24 @@ def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int, pipes: i
     usd = syn.random_state_dict(syn.unet_param_spec(), 0)  # generated once, shared by the engine instances
     pipe, (_, postproc) = etai.load_diffusion_model("synthetic-sd15", f"cuda:{local}", variant=prec, max_batch=4 * cobatch,
                                                     unet_state_dict=usd)
-    all_pipes = [pipe] + [clone_pipeline(pipe, usd) for _ in range(max(1, pipes) - 1)]  # groups in flight per GPU
+    all_pipes = [pipe] + [clone_pipeline(pipe) for _ in range(max(1, pipes) - 1)]  # groups in flight per GPU
     del usd
     for ci, combo in combos(spec):
         data = combo["data"] if isinstance(combo["data"], dict) else {"type": combo["data"]}
         n = min(int(data.get("n", 700)), limit) if limit else int(data.get("n", 700))
         out_dir = root / f"{ci:02d}_{combo['method']['type']}_{combo['edit_method']['type']}" / "imgs"
+        if skip_existing_dirs:  # eval.py:41-44 of the reference: a combination whose directory exists is skipped whole
+            exists = [out_dir.parent.exists()]
+            if world > 1:
+                dist.broadcast_object_list(exists, src=0)  # rank 0 decides before anybody creates the directory
+                dist.barrier()
+            if exists[0]:
+                if rank == 0:
+                    print(f"combo {ci}: {out_dir.parent} exists, skipped (--skip_existing_dirs)")
+                continue
         out_dir.mkdir(parents=True, exist_ok=True)
+        if rank == 0:
+            (out_dir.parent / "cfg.yaml").write_text(yaml.safe_dump(combo))  # eval.py:46-47
         method, edit_method = dict(combo["method"]), dict(combo["edit_method"])
 
         def make_editor(p):
@@ -115,7 +152,10 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser(description="Run an editing sweep sharded per image across the visible GPUs.")
     ap.add_argument("--cfg", required=True, help="Config file for evaluation.")
     ap.add_argument("--cobatch", type=int, default=4, help="Edits walked in lock step per GPU.")
+    ap.add_argument("--device", nargs="+", help="Which cuda devices to use. Can be multiple (one rank per device).")
+    ap.add_argument("--no_proc", action="store_true", help="Disables multiprocessing (runs in this process, first device).")
     ap.add_argument("--override", action="store_true", help="Override old results.")
+    ap.add_argument("--skip_existing_dirs", action="store_true", help="Skips existing directories.")
     ap.add_argument("--prec", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--limit", type=int, default=0, help="Only the first N samples (smoke runs).")
     ap.add_argument("--pipes", type=int, default=2, help="Lock-step groups in flight per GPU (each on its own engine).")

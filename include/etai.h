@@ -137,6 +137,12 @@ ETAI_EXPORT int etai_unet_create(etai_unet** out, const etai_unet_cfg* cfg, cons
                      int32_t device);
 ETAI_EXPORT int etai_unet_destroy(etai_unet* h);
 
+/* A second handle on the SAME packed device weights (read-only, reference counted: they are freed when the last handle
+ * that uses them is destroyed) with its own activation arena, CUDA graphs, staging buffers and stream.  Two lock-step
+ * groups in flight on one GPU (eval.py's per-GPU worker) then stream one copy of the 1.7 GB of
+ * weights instead of two.  max_batch <= 0 keeps the source's. */
+ETAI_EXPORT int etai_unet_clone(etai_unet** out, const etai_unet* src, int32_t max_batch);
+
 /* Pre-projects the text context through all 16 cross-attention to_k/to_v (the context is constant over a
  * whole loop: diffusion_inversion.py:411-413,432-434).  ctx: [B,77,768] of io_dtype. */
 ETAI_EXPORT int etai_unet_set_context(etai_unet* h, const void* ctx, int32_t io_dtype, int32_t B, void* stream);
@@ -203,6 +209,20 @@ ETAI_EXPORT int etai_attention(const void* q, const void* k, const void* v, void
                    int32_t heads, int32_t d, int32_t ldq, int32_t ldk, int32_t ldv, int32_t ldo, float scale,
                    const int32_t* q_row, const int32_t* k_row, const int32_t* v_row, int32_t dtype,
                    int32_t math_mode, void* stream);
+
+/* Cross-attention over the text context with the prompt-to-prompt control of ONE layer applied between softmax and PV
+ * (the control-aware attention the UNet runs at every attn2; exported for unit parity against an explicit
+ * softmax -> edit -> PV, modules/utils/ptp_utils.py:238-253 + modules/utils/ptp.py:205-274).
+ *   q:[B,N,ldq]; kv:[B,L,ldkv] with K of head h at column koff+h*d and V at voff+h*d; out:[B,N,ldo].
+ *   n_pairs > 0: rows edit_tgt_row[p] are edited from rows edit_base_row[p] with the pair's tables (etai_attn_ctrl).
+ *   n_store_rows > 0: store_acc[i][pix][w] += sum_heads P'[store_row[i]][head][pix][w]  (fp32 [n_store_rows,N,L]).
+ * workspace (16-bit path only): >= 327680 + heads*n_store_rows*N*L*4 bytes. */
+ETAI_EXPORT int etai_cross_attention(const void* q, const void* kv, void* out, int32_t B, int32_t N, int32_t L, int32_t heads,
+                         int32_t d, int32_t ldq, int32_t ldkv, int32_t ldo, int32_t koff, int32_t voff, float scale,
+                         int32_t n_pairs, const int32_t* edit_base_row, const int32_t* edit_tgt_row, const float* mapper,
+                         const float* blend_a, const float* equalizer, const float* alpha_step, int32_t n_store_rows,
+                         const int32_t* store_row, float* store_acc, int32_t dtype, int32_t math_mode, void* workspace,
+                         int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

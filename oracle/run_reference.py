@@ -62,7 +62,41 @@ SCENARIOS = {
     # EDICT: coupled latent pair, two UNet calls per step, exact inversion
     "edict_simple_4": (dict(type="edict", scheduler="ddim", num_inference_steps=4), "simple", {}, None, None),
     "edict_ptp_replace_3": (dict(type="edict", scheduler="ddim", num_inference_steps=3), "ptp", {}, PTP_REPLACE, None),
+    # the other mask modes of EtaInversion.get_mask (eta_inversion.py:159-205): maps read from the edit loop's own controller
+    # (bwd_source_target), direct-inversion leak to the target row (target_dirinv, masked by mask_dirinv), a soft mask
+    # (thres None + pow), and a user-supplied ("gt") mask that is bilinearly resized to 64x64 (eta_inversion.py:285-286)
+    "etainv_ptp_replace_bwdmask_3": (dict(type="etainv", scheduler="ddim", num_inference_steps=3, eta=(0.0, 0.4),
+                                          mask_mode_cfg=dict(mask_eta="bwd_source_target", mask_dirinv="fwd_mean",
+                                                             target_dirinv=0.5, thres=0.3)),
+                                     "ptp", {}, PTP_REPLACE, dict(edit_word_idx=(1, 1))),
+    "etainv_ptp_replace_gtmask_3": (dict(type="etainv", scheduler="ddim", num_inference_steps=3, eta=(0.0, 0.4),
+                                         mask_mode_cfg=dict(mask_eta="gt", thres=None, pow=2.0)),
+                                    "ptp", {}, PTP_REPLACE, dict(edit_word_idx=(1, 1), mask="GT_MASK")),
+    # BASELINE.json configs at their stated size (per-step tensors stored every KEEP_EVERY-th step to keep the fixture small)
+    "diffinv_simple_10": (dict(type="diffinv", scheduler="ddim", num_inference_steps=10), "simple", {}, None, None),
+    "etainv_ptp_replace_50": (dict(type="etainv", scheduler="ddim", num_inference_steps=50, eta=(0.0, 0.4)), "ptp", {},
+                              PTP_REPLACE, dict(edit_word_idx=(1, 1))),
+    "etainv_masactrl_50": (dict(type="etainv", scheduler="ddim", num_inference_steps=50, eta=(0.0, 0.4)), "masactrl", {},
+                           None, dict(edit_word_idx=(1, 1))),
+    # null-text inversion (null_text_inversion.py:42-101): per-step Adam on the uncond embedding, autograd through the UNet
+    "nti_ptp_replace_3": (dict(type="nti", scheduler="ddim", num_inference_steps=3, num_inner_steps=3), "ptp", {},
+                          PTP_REPLACE, None),
 }
+FULL_IMAGE = ("etainv_ptp_replace_5", "etainv_ptp_replace_50", "etainv_masactrl_50", "diffinv_simple_10",
+              "etainv_ptp_refine_3")
+KEEP_EVERY = 5  # scenarios with more than 10 steps keep step 0, 5, 10, ... and the last one
+
+
+def gt_mask() -> torch.Tensor:
+    """User-supplied 512x512 soft mask of the 'gt' mask mode: a smooth blob, values in [0, 1]."""
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, 512), torch.linspace(0, 1, 512), indexing="ij")
+    return torch.exp(-(((xx - 0.45) / 0.25) ** 2 + ((yy - 0.55) / 0.3) ** 2)).clamp(0, 1)
+
+
+def keep_steps(n: int):
+    if n <= 12:
+        return list(range(n))
+    return sorted(set(range(0, n, KEEP_EVERY)) | {n - 1})
 
 
 def _setup_paths():
@@ -103,6 +137,8 @@ def run_unet_fwd(pipe):
 def run_scenario(name, pipe, syn):
     import modules  # the reference's own package
     inv_kw, ed_type, ed_kw, cfg, inv_cfg = SCENARIOS[name]
+    if inv_cfg is not None and isinstance(inv_cfg.get("mask"), str):
+        inv_cfg = {**inv_cfg, "mask": gt_mask()}
     inverter = modules.load_inverter(model=pipe, **inv_kw)
     editor = modules.load_editor(inverter=inverter, type=ed_type, **ed_kw)
     image = syn.synthetic_image(0)
@@ -132,6 +168,16 @@ def run_scenario(name, pipe, syn):
             rec["picks"].append(idx[0])
             return r
         inverter.sample_variance_noise, inverter.get_eta_variance_noise = sample_vn, get_eta
+    # LocalBlend mask coverage per call (ptp.py:18-29), to prove the goldens exercise a non-trivial mask
+    from modules.utils import ptp as ref_ptp
+    lb_frac = []
+    orig_lb = ref_ptp.LocalBlend.get_mask
+
+    def lb_get_mask(self, x_t, maps, alpha, use_pool):
+        m = orig_lb(self, x_t, maps, alpha, use_pool)
+        lb_frac.append(m.float().mean(dim=(1, 2, 3)).tolist())
+        return m
+    ref_ptp.LocalBlend.get_mask = lb_get_mask
     orig_invert = inverter.invert
     inv_box = {}
 
@@ -141,22 +187,34 @@ def run_scenario(name, pipe, syn):
     inverter.invert = invert
 
     t0 = time.perf_counter()
-    with torch.no_grad():
+    with torch.no_grad():  # (NullTextInversion re-enables grad around its inner optimisation itself)
         res = editor.edit(image, SRC, TGT, cfg=None if cfg is None else {**cfg}, inv_cfg=inv_cfg)
     dt = time.perf_counter() - t0
+    ref_ptp.LocalBlend.get_mask = orig_lb
+    inv_lat = [as_tensor(l).detach().numpy() for l in inv_box["res"]["latents"]]
+    inv_eps = [e.detach().numpy() for e in inv_box["res"]["noise_preds"] if e is not None]
+    ki, kb = keep_steps(len(inv_lat)), keep_steps(len(rec["bwd_latents"]))
     out = dict(
-        inv_latents=np.stack([as_tensor(l).numpy() for l in inv_box["res"]["latents"]]),
-        inv_eps=np.stack([e.numpy() for e in inv_box["res"]["noise_preds"] if e is not None] or [np.zeros(0)]),
-        bwd_latents=np.stack(rec["bwd_latents"]), bwd_eps=np.stack(rec["bwd_eps"] or [np.zeros(0)]),
+        inv_latents=np.stack([inv_lat[i] for i in ki]), inv_steps_kept=np.array(ki),
+        inv_eps=np.stack([inv_eps[i] for i in keep_steps(len(inv_eps))] or [np.zeros(0)]),
+        bwd_latents=np.stack([rec["bwd_latents"][i] for i in kb]), bwd_steps_kept=np.array(kb),
+        bwd_eps=np.stack([rec["bwd_eps"][i] for i in keep_steps(len(rec["bwd_eps"]))] or [np.zeros(0)]),
         latent=as_tensor(res["latent"]).numpy(), latent_inv=as_tensor(res["latent_inv"]).numpy(),
         image_pool8=pool8(res["image"]), image_inv_pool8=pool8(res["image_inv"]),
         image_mean=np.array([res["image"].mean().item(), res["image_inv"].mean().item()]),
         seconds=np.array(dt),
     )
+    if lb_frac:
+        out["localblend_mask_fraction"] = np.array(lb_frac)
+    if name in FULL_IMAGE:  # PSNR gate of the 16-bit engine against the reference's fp32 image
+        out["image_f16"] = res["image"].to(torch.float16).numpy()
     if rec["picks"]:
         out["picks"] = np.array(rec["picks"], dtype=np.int64)
     if getattr(inverter, "attn_maps_forward", None):
         out["fwd_mean_map"] = inverter.attn_maps_forward["mean"][inv_cfg["edit_word_idx"][0]].numpy()
+        out["eta_mask_fraction"] = np.array(float((out["fwd_mean_map"] > 0.2).mean()))
+    if "uncond_embeddings" in inv_box["res"]:  # null-text inversion: the optimised embedding of every step
+        out["uncond_embeddings"] = np.stack([u.detach().numpy() for u in inv_box["res"]["uncond_embeddings"]])
     np.savez_compressed(GOLDEN / f"{name}.npz", **out)
     print(name, f"{dt:.1f}s", {k: v.shape for k, v in out.items()}, "picks", rec["picks"])
 

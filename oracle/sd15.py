@@ -643,14 +643,10 @@ class SyntheticTokenizer:
 
 
 def make_text_encoder(seed: int = 0):
-    """Random-init CLIP ViT-L/14 text tower (transformers); the same call is made by the product."""
-    from transformers import CLIPTextConfig, CLIPTextModel
-    cfg = CLIPTextConfig(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
-                         num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu")
-    with torch.random.fork_rng():
-        torch.manual_seed(seed)
-        m = CLIPTextModel(cfg)
-    return m.eval().requires_grad_(False)
+    """Random-init CLIP ViT-L/14 text tower (transformers); the synthetic init is an INPUT definition shared with the
+    product (eta_inversion_b200/synthetic.py), like the random UNet / VAE state dicts."""
+    from eta_inversion_b200.synthetic import make_text_encoder as mk
+    return mk(seed)
 
 
 class StableDiffusionPipeline:

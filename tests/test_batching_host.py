@@ -110,3 +110,37 @@ def test_lanes_that_disagree_fail_loudly():
     [t.start() for t in ths]
     [t.join() for t in ths]
     assert len(errs) == 2 and all("lanes disagree" in e for e in errs)
+
+
+def test_a_lane_that_finishes_early_releases_its_peers():
+    """An edit that returns early (EtaInversion.invert -> None for an unsupported sample, eta_inversion.py:385-386, or
+    a loop with fewer UNet forwards) must not strand the other lanes: they go on with a smaller merged batch."""
+    from eta_inversion_b200 import batching
+
+    eng = _StubEngine()
+    pipe = SimpleNamespace(unet=eng, device=torch.device("cpu"))
+
+    class _Editor:
+        def __init__(self, p):
+            self.unet = p.unet
+
+        def edit(self, lane, steps):
+            if steps == 0:
+                return None                     # "unsupported": no UNet forward at all
+            x = torch.full((2, 4, 8, 8), float(lane))
+            ctx = torch.full((2, 77, 8), float(lane))
+            for s in range(steps):
+                x = self.unet(x, 981 - s, encoder_hidden_states=ctx)["sample"]
+            return x
+
+    orig_set_device = torch.cuda.set_device
+    torch.cuda.set_device = lambda d: None      # CPU-only test: run_lockstep pins the device in every lane thread
+    try:
+        res = batching.run_lockstep(pipe, [dict(lane=0, steps=3), dict(lane=1, steps=0), dict(lane=2, steps=2)], _Editor)
+    finally:
+        torch.cuda.set_device = orig_set_device
+    assert res[1] is None
+    # steps 0,1: lanes 0 and 2 share a B=4 forward; step 2: lane 0 alone (B=2)
+    assert [c[0].shape[0] for c in eng.calls] == [4, 4, 2]
+    assert res[0][:, 0, 0, 0].tolist() == [0.0, 3.0]            # rows 0,1 in every forward
+    assert res[2][:, 0, 0, 0].tolist() == [2.0 + 2 * 2, 2.0 + 2 * 3]  # rows 2,3 of the two shared forwards
