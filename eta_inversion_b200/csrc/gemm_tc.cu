@@ -11,7 +11,10 @@
 // CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global).  smem ring of STAGES x (A 128x64 + B BNx64).
 // UMMA shape 128 x BN x 16 (cta_group::1), BN in {128, 160}.  Roofline: tensor pipe.
+#include <algorithm>
 #include <mutex>
+#include <vector>
+#include <cstdlib>
 #include <cstring>
 #include "ops.cuh"
 #include "tc_common.cuh"
@@ -74,7 +77,9 @@ struct TcParams {
     int cin_blocks;        // Cin / 64
     int Himg, Wimg;        // output == input spatial size (stride 1)
     int fmt;               // 0 f16, 1 bf16
+    long long* trace;      // debugging aid (ETAI_GEMM_TRACE=1): per-CTA, per-tile clock64() stamps of the three roles
 };
+constexpr int TRACE_TILES = 64, TRACE_SLOTS = 8;
 
 // ---- epilogue helpers -----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, uint32_t (&r)[32]) {  // no wait: pair with tmem_wait_ld()
@@ -130,13 +135,24 @@ struct Smem {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_BYTES = 8 * 2 * 32 * 64;  // 8 epilogue warps x 2 buffers x [32 rows x 32 cols] 16-bit
-    static constexpr int STAGES = (190 * 1024) / STAGE_BYTES > 6 ? 6 : (190 * 1024) / STAGE_BYTES;
+    // Epilogue staging: one pass of PW accumulator columns of all 128 rows, as column panels of 64 16-bit columns
+    // ([128 rows][128 B], 128B-swizzled, so the row-per-lane writes are conflict free) plus a narrow tail panel; it leaves
+    // through ONE TMA store per panel.  (Round 1 used a [32 x 32] box per warp and chunk: 20 store instructions per
+    // 128 x 160 tile cost the SM's TMA unit as much time as the tile's operand loads -- ETAI_GEMM_TRACE, r02_gemm_trace.)
+    static constexpr int PW = BN == 320 ? 160 : BN;            // accumulator columns per pass (a 320-wide tile takes two)
+    static constexpr int PASSES = BN / PW;
+    static constexpr int EPI_BYTES = (PW / 64) * 16384 + (PW % 64 ? 8192 : 0);
+    static constexpr int STAGES = (227 * 1024 - EPI_BYTES - 2048) / STAGE_BYTES > 6 ? 6 : (227 * 1024 - EPI_BYTES - 2048) / STAGE_BYTES;
     static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
     static constexpr int BAR_OFF = EPI_OFF + EPI_BYTES;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + slack for manual 1024-B alignment
-    static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;  // TMEM columns between the two accumulator buffers
-    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+    // BN = 320 is issued as two UMMAs of N = 160 per k-step into two accumulators that sit side by side in TMEM (columns
+    // [0,160) and [160,320)), so the epilogue sees one 320-column tile.  It is single-buffered (2 x 320 > 512 columns).
+    static constexpr int UN = BN == 320 ? 160 : BN;            // UMMA N
+    static constexpr int NACC = BN / UN;                       // UMMAs per k-step
+    static constexpr int NBUF = BN == 320 ? 1 : 2;             // accumulator buffers in TMEM
+    static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;   // TMEM columns between the accumulator buffers (NBUF = 2)
+    static constexpr int TMEM_COLS = BN == 320 ? 512 : 2 * ACC_STRIDE;
 };
 
 // Persistent kernel: grid = min(#work items, #SMs); every role walks the same static schedule
@@ -146,7 +162,8 @@ struct Smem {
 template <typename T, int BN, bool CONV>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-          const __grid_constant__ CUtensorMap tmC, const __grid_constant__ TcParams p) {
+          const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
+          const __grid_constant__ TcParams p) {
     using S = Smem<BN>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -163,8 +180,9 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
         prefetch_tmap(&tmC);
+        prefetch_tmap(&tmC2);
         for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS); }
+        for (int b = 0; b < S::NBUF; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
@@ -189,6 +207,8 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = kb0 + p.kb_per_split < p.num_kb ? kb0 + p.kb_per_split : p.num_kb;
+                const int tli = (item - blockIdx.x) / gridDim.x;
+                if (p.trace && tli < TRACE_TILES) p.trace[((long)blockIdx.x * TRACE_TILES + tli) * TRACE_SLOTS + 0] = clock64();
                 for (int kb = kb0; kb < kb1; ++kb, ++kc) {
                     int s = kc % S::STAGES;
                     uint32_t ph = (kc / S::STAGES) & 1;
@@ -202,227 +222,268 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     } else {
                         tma_load_2d(sa, &tmA, &full[s], kb * BK, (int)m0);
                     }
-                    tma_load_2d(sb, &tmB, &full[s], kb * BK, n0);
+#pragma unroll
+                    for (int j = 0; j < S::NACC; ++j)  // a TMA box has at most 256 rows: one box per UMMA-N slice of the tile
+                        tma_load_2d(sb + j * S::UN * 128, &tmB, &full[s], kb * BK, n0 + j * S::UN);
                 }
+                if (p.trace && tli < TRACE_TILES) p.trace[((long)blockIdx.x * TRACE_TILES + tli) * TRACE_SLOTS + 1] = clock64();
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer =====
-            const uint32_t idesc = make_idesc_f16(p.fmt, BM, BN);
+            const uint32_t idesc = make_idesc_f16(p.fmt, BM, S::UN);
             int kc = 0, li = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
                 const int split = item / (p.tiles_m * p.tiles_n);
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = kb0 + p.kb_per_split < p.num_kb ? kb0 + p.kb_per_split : p.num_kb;
-                const int buf = li & 1;
-                mbar_wait(&acc_empty[buf], ((li >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+                const int buf = li % S::NBUF;
+                long long* tr = (p.trace && li < TRACE_TILES) ? p.trace + ((long)blockIdx.x * TRACE_TILES + li) * TRACE_SLOTS : nullptr;
+                if (tr) tr[2] = clock64();
+                mbar_wait(&acc_empty[buf], ((li / S::NBUF) & 1) ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
+                if (tr) tr[3] = clock64();
                 const uint32_t tacc = tmem_base + (uint32_t)buf * S::ACC_STRIDE;
                 for (int kb = kb0; kb < kb1; ++kb, ++kc) {
                     int s = kc % S::STAGES;
                     uint32_t ph = (kc / S::STAGES) & 1;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
+                    if (tr && kb == kb0) tr[4] = clock64();
                     uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES);
                     uint64_t da = make_smem_desc_sw128(sa);
                     uint64_t db = make_smem_desc_sw128(sa + S::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 16 elements (32 B) along K inside the 128-B swizzle atom: +2 in the (addr>>4) field
-                        umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0) || (k > 0));
+                        // advance 16 elements (32 B) along K inside the 128-B swizzle atom: +2 in the (addr>>4) field;
+                        // accumulator j takes rows [j*UN, (j+1)*UN) of the B stage (UN * 128 B further on)
+#pragma unroll
+                        for (int j = 0; j < S::NACC; ++j)
+                            umma_f16(tacc + (uint32_t)(j * S::UN), da + (uint64_t)(2 * k),
+                                     db + (uint64_t)(j * (S::UN * 128 >> 4) + 2 * k), idesc, (kb > kb0) || (k > 0));
                     }
                     umma_commit(&empty[s]);  // frees the smem stage once these MMAs retire
                 }
                 umma_commit(&acc_full[buf]);
+                if (tr) tr[5] = clock64();
             }
         }
     } else {
-        // ===== epilogue: warps 2..9.  TMEM lane quarter = warp % 4; the two warps of a quarter alternate 32-col chunks.
-        // Every warp owns a private double-buffered [32 rows x 32 cols] 16-bit staging tile and writes it with its own TMA
-        // store (box 32 x 32; rows/cols beyond M/N are clipped by the tensor map): no cross-warp barrier in the epilogue.
+        // ===== epilogue: warps 2..9 (256 threads).  TMEM lane quarter = warp % 4 = 32 rows of the tile, one row per lane;
+        // the two warps of a quarter alternate 32-column chunks.  Per pass: wait until the staging panels are free, every
+        // warp converts its chunks (TMEM -> registers -> bias / residual / GEGLU -> 16 bit) into the panels, one named
+        // barrier, then one thread issues one TMA store per panel (rows / columns beyond M / N are clipped by the map).
         const int quarter = warp & 3;
         const int half = (warp - 2) >> 2;
+        const int trow = quarter * 32 + lane;  // row inside the tile == TMEM lane
         const T* bias = reinterpret_cast<const T*>(p.bias);
         const T* res = reinterpret_cast<const T*>(p.residual);
-        unsigned char* stage_base = smem + S::EPI_OFF + (warp - 2) * (2 * 32 * 64);
-        int li = 0, chunk_ctr = 0;
+        const uint32_t epi = smem_u32(smem + S::EPI_OFF);
+        const bool leader = warp == 2 && lane == 0;
+        constexpr int PW = S::PW;
+        int li = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
             const int tile = item % (p.tiles_m * p.tiles_n), split = item / (p.tiles_m * p.tiles_n);
             const int n0 = (tile % p.tiles_n) * BN;
             const long m0 = (long)(tile / p.tiles_n) * BM;
-            const int buf = li & 1;
-            mbar_wait(&acc_full[buf], (li >> 1) & 1);
-            tc_fence_after();
-            const long m = m0 + quarter * 32 + lane;
+            const int buf = li % S::NBUF;
+            const long m = m0 + trow;
             const bool row_ok = m < p.M;
+            const bool lean = !p.partial && !p.bias2;
+            const T* brow = bias ? bias + n0 : nullptr;
+            const T* rrow = (res && row_ok && !p.geglu) ? res + m * p.ldr + n0 : nullptr;
+            // bias / residual of a chunk are requested one chunk ahead -- the first chunk's before the accumulator is even
+            // complete -- so their L2 / HBM latency is off the epilogue's critical path
+            uint4 b4n[4], r4n[4];
+            auto prefetch = [&](int c0) {
+                if (n0 + c0 < p.N) {
+                    if (brow) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) b4n[j] = ldg128(brow + c0 + 8 * j);
+                    }
+                    if (rrow) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) r4n[j] = ldg128(rrow + c0 + 8 * j);
+                    }
+                }
+            };
+            // stage 16-byte piece `piece` (of the pass's output row) of this lane's row
+            auto stage16 = [&](int piece, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+                const int panel = piece >> 3, pp = piece & 7;           // 8 pieces = 64 columns = one 128-byte panel row
+                constexpr int FULL = (PW / 64);                         // number of full (swizzled) panels when not GEGLU
+                const int full = p.geglu ? (PW / 2) / 64 : FULL;
+                uint32_t addr;
+                if (panel < full) addr = epi + (uint32_t)panel * 16384u + (uint32_t)trow * 128u + (uint32_t)((pp ^ (trow & 7)) << 4);
+                else {  // tail panel: dense rows of 64 B (32 columns) or, for GEGLU at PW = 160, 32 B (16 columns)
+                    const uint32_t rowb = p.geglu ? 32u : 64u;
+                    addr = epi + (uint32_t)full * 16384u + (uint32_t)trow * rowb + (uint32_t)(pp << 4);
+                }
+                sts128(addr, a, b, c, d);
+            };
+            if (lean) prefetch(half * 32);
+            mbar_wait(&acc_full[buf], (li / S::NBUF) & 1);
+            tc_fence_after();
+            long long* tr = (p.trace && li < TRACE_TILES && leader)
+                                ? p.trace + ((long)blockIdx.x * TRACE_TILES + li) * TRACE_SLOTS : nullptr;
+            if (tr) tr[6] = clock64();
             const uint32_t tacc = tmem_base + (uint32_t)buf * S::ACC_STRIDE + ((uint32_t)(quarter * 32) << 16);
-            // ---- lean paths (the bulk of the UNet's GEMMs).  For K = 320..640 the main loop of a tile is < 1 us and the
-            // epilogue sets the pace; it is bound by instruction latency with two warps per scheduler, so: operands stay
-            // packed (one F2FP per pair, packed adds), bias / residual loads are issued under the TMEM load, staging
-            // goes through st.shared.v4, and address arithmetic is hoisted out of the chunk loop.
-            if (!p.partial && !p.bias2) {
-                const uint32_t sbase = smem_u32(stage_base) + (uint32_t)lane * (p.geglu ? 32u : 64u);
-                const T* brow = bias ? bias + n0 : nullptr;
-                const T* rrow = (res && row_ok && !p.geglu) ? res + m * p.ldr + n0 : nullptr;
 #pragma unroll 1
-                for (int c0 = half * 32; c0 < BN; c0 += 64) {
-                    uint32_t r[32];
-                    tmem_ld32_raw(tacc + (uint32_t)c0, r);  // warp-collective
-                    const bool col_ok = n0 + c0 < p.N;      // warp-uniform
-                    uint4 b4[4], r4[4];
-                    if (col_ok && brow) {
+            for (int ps = 0; ps < S::PASSES; ++ps) {
+                const int hh = (ps & 1) ? half ^ 1 : half;  // the second pass swaps roles: 3 + 2 and 2 + 3 chunks per warp
+                if (!p.partial) {
+                    if (ps > 0 && lean) prefetch(ps * PW + hh * 32);
+                    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous stores have read the panels
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                }
+#pragma unroll 1
+                for (int cc = hh * 32; cc < PW; cc += 64) {
+                    const int c0 = ps * PW + cc;            // accumulator column inside the tile
+                    const int n = n0 + c0;
+                    const bool col_ok = n < p.N;            // warp-uniform
+                    if (lean) {
+                        // ---- lean path (the bulk of the UNet's GEMMs): operands stay packed (one F2FP per pair, packed adds)
+                        uint32_t r[32];
+                        tmem_ld32_raw(tacc + (uint32_t)c0, r);  // warp-collective
+                        uint4 b4[4], r4[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) b4[j] = ldg128(brow + c0 + 8 * j);
-                    }
-                    if (col_ok && rrow) {
+                        for (int j = 0; j < 4; ++j) { b4[j] = b4n[j]; r4[j] = r4n[j]; }
+                        if (cc + 64 < PW) prefetch(c0 + 64);
+                        tmem_wait_ld();
+                        if (!col_ok) continue;
+                        if (p.geglu) {
+                            // (value, gate) column pairs; bias in fp32 (it feeds the nonlinearity)
+                            uint32_t h[8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) r4[j] = ldg128(rrow + c0 + 8 * j);
+                            for (int j = 0; j < 4; ++j) {
+                                float bf[8];
+                                if (brow) {
+                                    const Pack<T, 8>& pk = *reinterpret_cast<const Pack<T, 8>*>(&b4[j]);
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) bf[i] = to_f<T>(pk.v[i]);
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 8; ++i) bf[i] = 0.f;
+                                }
+                                float o[4];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+                                    o[i] = (__uint_as_float(r[8 * j + 2 * i]) + bf[2 * i]) *
+                                           gelu_fast(__uint_as_float(r[8 * j + 2 * i + 1]) + bf[2 * i + 1]);
+                                h[2 * j] = pack2<T>(o[0], o[1]);
+                                h[2 * j + 1] = pack2<T>(o[2], o[3]);
+                            }
+                            const int piece = cc >> 4;  // 16 output columns = 2 pieces
+                            stage16(piece, h[0], h[1], h[2], h[3]);
+                            stage16(piece + 1, h[4], h[5], h[6], h[7]);
+                        } else {
+                            uint32_t h[16];
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) h[i] = pack2<T>(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+                            if (brow) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    h[4 * j] = add2<T>(h[4 * j], b4[j].x); h[4 * j + 1] = add2<T>(h[4 * j + 1], b4[j].y);
+                                    h[4 * j + 2] = add2<T>(h[4 * j + 2], b4[j].z); h[4 * j + 3] = add2<T>(h[4 * j + 3], b4[j].w);
+                                }
+                            }
+                            if (rrow) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    h[4 * j] = add2<T>(h[4 * j], r4[j].x); h[4 * j + 1] = add2<T>(h[4 * j + 1], r4[j].y);
+                                    h[4 * j + 2] = add2<T>(h[4 * j + 2], r4[j].z); h[4 * j + 3] = add2<T>(h[4 * j + 3], r4[j].w);
+                                }
+                            }
+                            const int piece = cc >> 3;  // 32 output columns = 4 pieces
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) stage16(piece + j, h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                        }
+                        continue;
                     }
-                    tmem_wait_ld();
+                    // ---- generic path: split-K partials, fp32 time-embedding bias (resnet conv1) ----
+                    float v[32];
+                    tmem_ld32(tacc + (uint32_t)c0, v);  // warp-collective
                     if (!col_ok) continue;
-                    const uint32_t sbuf = sbase + (uint32_t)(chunk_ctr & 1) * (32 * 64);
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // buffer used 2 chunks ago is free
-                    __syncwarp();
+                    if (p.partial) {  // split-K: raw fp32 partial sums, epilogue happens in splitk_reduce_k
+                        if (row_ok) {
+                            float* dst = p.partial + ((long)split * p.M + m) * p.N + n;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                        continue;
+                    }
+                    if (bias) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            float b8[8];
+                            load8<T>(bias + n + j, b8);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[j + i] += b8[i];
+                        }
+                    }
+                    if (p.bias2) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            float4 b4 = *reinterpret_cast<const float4*>(p.bias2 + n + j);
+                            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                        }
+                    }
+                    if (res && row_ok && !p.geglu) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            float r8[8];
+                            load8<T>(res + m * p.ldr + n + j, r8);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[j + i] += r8[i];
+                        }
+                    }
                     if (p.geglu) {
-                        // (value, gate) column pairs; bias in fp32 (it feeds the nonlinearity)
                         uint32_t h[8];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float bf[8];
-                            if (brow) {
-                                const Pack<T, 8>& pk = *reinterpret_cast<const Pack<T, 8>*>(&b4[j]);
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) bf[i] = to_f<T>(pk.v[i]);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < 8; ++i) bf[i] = 0.f;
-                            }
-                            float o[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-                                o[i] = (__uint_as_float(r[8 * j + 2 * i]) + bf[2 * i]) *
-                                       gelu_fast(__uint_as_float(r[8 * j + 2 * i + 1]) + bf[2 * i + 1]);
-                            h[2 * j] = pack2<T>(o[0], o[1]);
-                            h[2 * j + 1] = pack2<T>(o[2], o[3]);
-                        }
-                        sts128(sbuf, h[0], h[1], h[2], h[3]);
-                        sts128(sbuf + 16, h[4], h[5], h[6], h[7]);
+                        for (int i = 0; i < 8; ++i)
+                            h[i] = pack2<T>(v[4 * i] * gelu_f(v[4 * i + 1]), v[4 * i + 2] * gelu_f(v[4 * i + 3]));
+                        const int piece = cc >> 4;
+                        stage16(piece, h[0], h[1], h[2], h[3]);
+                        stage16(piece + 1, h[4], h[5], h[6], h[7]);
                     } else {
                         uint32_t h[16];
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) h[i] = pack2<T>(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-                        if (brow) {
+                        for (int i = 0; i < 16; ++i) h[i] = pack2<T>(v[2 * i], v[2 * i + 1]);
+                        const int piece = cc >> 3;
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                h[4 * j] = add2<T>(h[4 * j], b4[j].x); h[4 * j + 1] = add2<T>(h[4 * j + 1], b4[j].y);
-                                h[4 * j + 2] = add2<T>(h[4 * j + 2], b4[j].z); h[4 * j + 3] = add2<T>(h[4 * j + 3], b4[j].w);
-                            }
-                        }
-                        if (rrow) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                h[4 * j] = add2<T>(h[4 * j], r4[j].x); h[4 * j + 1] = add2<T>(h[4 * j + 1], r4[j].y);
-                                h[4 * j + 2] = add2<T>(h[4 * j + 2], r4[j].z); h[4 * j + 3] = add2<T>(h[4 * j + 3], r4[j].w);
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) sts128(sbuf + 16 * j, h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                        for (int j = 0; j < 4; ++j) stage16(piece + j, h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                }
+                if (ps == S::PASSES - 1) {
+                    tc_fence_before();  // TMEM reads of this accumulator are done
                     __syncwarp();
-                    if (lane == 0) {
-                        const int n = n0 + c0;
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                                         reinterpret_cast<uint64_t>(&tmC)),
-                                     "r"(sbuf - (uint32_t)lane * (p.geglu ? 32u : 64u)), "r"(p.geglu ? n / 2 : n),
-                                     "r"((int)(m0 + quarter * 32))
-                                     : "memory");
+                    if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                }
+                if (!p.partial) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // panel writes -> visible to the TMA unit
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (leader) {
+                        const int pwo = p.geglu ? PW / 2 : PW;                    // output columns of this pass
+                        const int ncol0 = (p.geglu ? n0 / 2 : n0) + ps * pwo;
+                        const int nout = p.geglu ? p.N / 2 : p.N;
+                        const int full = pwo / 64;
+                        for (int k = 0; k < full; ++k)
+                            if (ncol0 + k * 64 < nout)
+                                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                                 reinterpret_cast<uint64_t>(&tmC)), "r"(epi + (uint32_t)k * 16384u),
+                                             "r"(ncol0 + k * 64), "r"((int)m0) : "memory");
+                        if ((pwo & 63) && ncol0 + full * 64 < nout)
+                            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                                             reinterpret_cast<uint64_t>(&tmC2)), "r"(epi + (uint32_t)full * 16384u),
+                                         "r"(ncol0 + full * 64), "r"((int)m0) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
-                    ++chunk_ctr;
                 }
-            } else
-            // ---- generic path: split-K partials, fp32 time-embedding bias (resnet conv1) ----
-#pragma unroll 1
-            for (int c0 = half * 32; c0 < BN; c0 += 64) {
-                float v[32];
-                tmem_ld32(tacc + (uint32_t)c0, v);  // warp-collective
-                const int n = n0 + c0;
-                if (n >= p.N) continue;             // warp-uniform
-                if (p.partial) {  // split-K: raw fp32 partial sums, epilogue happens in splitk_reduce_k
-                    if (row_ok) {
-                        float* dst = p.partial + ((long)split * p.M + m) * p.N + n;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    }
-                    continue;
-                }
-                if (bias) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float b8[8];
-                        load8<T>(bias + n + j, b8);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[j + i] += b8[i];
-                    }
-                }
-                if (p.bias2) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        float4 b4 = *reinterpret_cast<const float4*>(p.bias2 + n + j);
-                        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-                    }
-                }
-                if (res && row_ok && !p.geglu) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float r8[8];
-                        load8<T>(res + m * p.ldr + n + j, r8);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[j + i] += r8[i];
-                    }
-                }
-                // ---- stage in this warp's private buffer, then TMA store ----
-                unsigned char* sbuf = stage_base + (chunk_ctr & 1) * (32 * 64);
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // buffer used 2 chunks ago is free
-                __syncwarp();
-                if (p.geglu) {
-                    float o8[8];
-                    T* dst = reinterpret_cast<T*>(sbuf + lane * 32);
-#pragma unroll
-                    for (int j = 0; j < 16; j += 8) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) o8[i] = v[2 * (j + i)] * gelu_f(v[2 * (j + i) + 1]);
-                        store8<T>(dst + j, o8);
-                    }
-                } else {
-                    T* dst = reinterpret_cast<T*>(sbuf + lane * 64);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float o8[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) o8[i] = v[j + i];
-                        store8<T>(dst + j, o8);
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) {
-                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
-                                     reinterpret_cast<uint64_t>(&tmC)),
-                                 "r"(smem_u32(sbuf)), "r"(p.geglu ? n / 2 : n), "r"((int)(m0 + quarter * 32))
-                                 : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                }
-                ++chunk_ctr;
             }
-            tc_fence_before();  // TMEM reads of this accumulator are done
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+            if (tr) tr[7] = clock64();
         }
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -465,6 +526,11 @@ __global__ void splitk_reduce_k(const float* __restrict__ partial, int splits, T
     }
 }
 
+bool gemm_tc_bn320_disabled() {
+    static const bool v = [] { const char* e = getenv("ETAI_GEMM_NO_BN320"); return e && e[0] == '1'; }();
+    return v;
+}
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -477,7 +543,8 @@ int num_sms() {
 }
 
 template <typename T, int BN, bool CONV>
-void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const TcParams& p, cudaStream_t s) {
+void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2, const TcParams& p,
+            cudaStream_t s) {
     using S = Smem<BN>;
     static bool configured = false;
     if (!configured) {
@@ -486,7 +553,39 @@ void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& t
     }
     int items = p.tiles_m * p.tiles_n * p.splits;
     int grid = items < num_sms() ? items : num_sms();
-    gemm_tc_k<T, BN, CONV><<<grid, GT_THREADS, S::TOTAL, s>>>(tmA, tmB, tmC, p);
+    static const bool trace = [] { const char* e = getenv("ETAI_GEMM_TRACE"); return e && e[0] == '1'; }();
+    if (trace) {  // debugging aid: synchronous, prints the mean per-tile timeline of CTA 0 and of all CTAs
+        TcParams q = p;
+        size_t n = (size_t)grid * TRACE_TILES * TRACE_SLOTS;
+        CUDA_CHECK(cudaMalloc((void**)&q.trace, n * sizeof(long long)));
+        CUDA_CHECK(cudaMemset(q.trace, 0, n * sizeof(long long)));
+        gemm_tc_k<T, BN, CONV><<<grid, GT_THREADS, S::TOTAL, s>>>(tmA, tmB, tmC, tmC2, q);
+        CUDA_CHECK(cudaStreamSynchronize(s));
+        std::vector<long long> h(n);
+        CUDA_CHECK(cudaMemcpy(h.data(), q.trace, n * sizeof(long long), cudaMemcpyDeviceToHost));
+        CUDA_CHECK(cudaFree(q.trace));
+        double sum[6] = {0}; long cnt = 0;
+        for (int c = 0; c < grid; ++c) {
+            int nt = (items - c + grid - 1) / grid; if (nt > TRACE_TILES) nt = TRACE_TILES;
+            for (int t = 1; t + 1 < nt; ++t) {  // steady state: skip the first and the last tile
+                const long long* r = &h[((size_t)c * TRACE_TILES + t) * TRACE_SLOTS];
+                const long long* rn = r + TRACE_SLOTS;
+                sum[0] += (double)(rn[2] - r[2]);   // tile period at the MMA thread
+                sum[1] += (double)(r[3] - r[2]);    // wait for the accumulator buffer
+                sum[2] += (double)(r[4] - r[3]);    // wait for the first k-block
+                sum[3] += (double)(r[5] - r[4]);    // issue of the main loop (first k-block landed -> last commit)
+                sum[4] += (double)(r[7] - r[6]);    // epilogue (accumulator complete -> buffer released)
+                sum[5] += (double)(r[1] - r[0]);    // producer: first empty-wait -> last TMA issue of the tile
+                ++cnt;
+            }
+        }
+        if (cnt)
+            printf("gemm_tc trace BN=%d conv=%d M=%ld N=%d kb=%d tiles/CTA=%.1f | cycles per tile: period %.0f, acc wait %.0f, "
+                   "first-kb wait %.0f, mainloop issue %.0f, epilogue %.0f, producer %.0f\n", BN, (int)CONV, p.M, p.N, p.num_kb,
+                   (double)items / grid, sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, sum[4] / cnt, sum[5] / cnt);
+        return;
+    }
+    gemm_tc_k<T, BN, CONV><<<grid, GT_THREADS, S::TOTAL, s>>>(tmA, tmB, tmC, tmC2, p);
     KERNEL_CHECK();
     if (p.partial) {
         long total = p.M * p.N / 4;
@@ -535,15 +634,32 @@ void gemm_tc(const GemmArgs& a0, void* ws, size_t ws_bytes, cudaStream_t s) {
     p.C = a.C; p.bias = a.bias; p.bias2 = (const float*)a.rowbias; p.residual = a.residual;
     p.M = a.M; p.N = a.N; p.ldc = a.ldc; p.ldr = a.ldr; p.geglu = a.geglu;
     p.fmt = a.dtype == ETAI_BF16 ? 1 : 0;
-    const int BN = (a.N % 160 == 0) ? 160 : 128;
+    // Tile width.  One SM's TMA unit delivers a 128-byte operand row every ~1.7 cycles (scripts/ubench/tma_rate.cu,
+    // profiles/r02_tma_rate.txt), so a 128 x 160 tile (288 rows per k-block for 320 MMA cycles) is TMA-bound at ~60 % of the
+    // tensor pipe; 128 x 320 (448 rows for 640 MMA cycles) loads A once per 320 columns.  It is used when it still fills
+    // the SMs (or split-K will).
     p.tiles_m = cdiv(a.M, BM);
+    int BN = (a.N % 160 == 0) ? 160 : 128;
+    if (a.N % 320 == 0 && !gemm_tc_bn320_disabled()) {
+        // Cost model in SM cycles per CTA, fitted to profiles/r02_ops_*.txt (M = 4096..65536, K = 320..5120): a 128 x 160
+        // tile costs ~590 cycles per k-block (TMA-bound) + ~3000 per tile; a 128 x 320 tile ~930 per k-block + ~9900 per tile
+        // (its accumulators are single-buffered, so the epilogue is exposed).  Per unit of work the wide tile wins from
+        // K ~ 1000 on -- every conv3x3 (K >= 2880) and the K >= 1280 projections -- unless wave quantisation says otherwise.
+        const long t320 = (long)p.tiles_m * (a.N / 320), t160 = 2 * t320;
+        const long nk = (a.conv ? 9 * a.Cin : a.K) / BK;
+        auto waves = [&](long tiles) { return (long)cdiv(tiles, num_sms()); };
+        const long c160 = waves(t160) * (590 * nk + 3000), c320 = waves(t320) * (930 * nk + 9900);
+        const bool splitk320 = t320 * 2 <= num_sms() && nk >= 36 && ws != nullptr;
+        static const bool force = [] { const char* e = getenv("ETAI_GEMM_FORCE_BN320"); return e && e[0] == '1'; }();
+        if (force || splitk320 || c320 < c160) BN = 320;
+    }
     p.tiles_n = cdiv(a.N, BN);
 
     CUtensorMap tmA, tmB;
     {
         uint64_t dims[2] = {(uint64_t)a.K, (uint64_t)a.N};
         uint64_t str[1] = {(uint64_t)a.K * 2};
-        uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+        uint32_t box[2] = {(uint32_t)BK, (uint32_t)(BN == 320 ? 160 : BN)};
         tmB = make_tmap_16bit(a.W, a.dtype, 2, dims, str, box);
     }
     if (a.conv) {
@@ -562,13 +678,17 @@ void gemm_tc(const GemmArgs& a0, void* ws, size_t ws_bytes, cudaStream_t s) {
         tmA = make_tmap_16bit(a.A, a.dtype, 2, dims, str, box);
         p.num_kb = a.K / BK;
     }
-    CUtensorMap tmC;
+    // C leaves in column panels: 64-column panels ([128 rows][128 B], 128B swizzle) through tmC and, when the pass width is
+    // not a multiple of 64 output columns, a narrow dense tail panel (32 columns, or 16 for GEGLU) through tmC2
+    CUtensorMap tmC, tmC2;
     {
         const int n_out = a.geglu ? a.N / 2 : a.N;
         uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)a.M};
         uint64_t str[1] = {(uint64_t)a.ldc * 2};
-        uint32_t box[2] = {(uint32_t)(a.geglu ? 16 : 32), 32};  // one warp's sub-tile
-        tmC = make_tmap_16bit(a.C, a.dtype, 2, dims, str, box, /*swizzle128=*/false);
+        uint32_t box[2] = {64, 128};
+        tmC = make_tmap_16bit(a.C, a.dtype, 2, dims, str, box, /*swizzle128=*/true);
+        uint32_t box2[2] = {(uint32_t)(a.geglu ? 16 : 32), 128};
+        tmC2 = make_tmap_16bit(a.C, a.dtype, 2, dims, str, box2, /*swizzle128=*/false);
     }
     // split-K for the low-resolution layers (few output tiles, K up to 23040): fill the SMs with K slices, fp32
     // partials in the workspace, fixed-order reduction + epilogue in a second launch
@@ -589,12 +709,15 @@ void gemm_tc(const GemmArgs& a0, void* ws, size_t ws_bytes, cudaStream_t s) {
     }
 #define LAUNCH(T)                                                            \
     do {                                                                     \
-        if (BN == 160) {                                                     \
-            if (a.conv) launch<T, 160, true>(tmA, tmB, tmC, p, s);           \
-            else launch<T, 160, false>(tmA, tmB, tmC, p, s);                 \
+        if (BN == 320) {                                                     \
+            if (a.conv) launch<T, 320, true>(tmA, tmB, tmC, tmC2, p, s);           \
+            else launch<T, 320, false>(tmA, tmB, tmC, tmC2, p, s);                 \
+        } else if (BN == 160) {                                              \
+            if (a.conv) launch<T, 160, true>(tmA, tmB, tmC, tmC2, p, s);           \
+            else launch<T, 160, false>(tmA, tmB, tmC, tmC2, p, s);                 \
         } else {                                                             \
-            if (a.conv) launch<T, 128, true>(tmA, tmB, tmC, p, s);           \
-            else launch<T, 128, false>(tmA, tmB, tmC, p, s);                 \
+            if (a.conv) launch<T, 128, true>(tmA, tmB, tmC, tmC2, p, s);           \
+            else launch<T, 128, false>(tmA, tmB, tmC, tmC2, p, s);                 \
         }                                                                    \
     } while (0)
     if (a.dtype == ETAI_F16) LAUNCH(__half);

@@ -10,9 +10,268 @@
 //      in shared memory, then normalises + affine (+SiLU) its slice with 16-byte loads/stores.
 // Algorithmic bytes: read x + write y (2*elements*sizeof); the second read of x in (2) hits L2 for UNet-sized
 // tensors (<= 10.5 MB per row in fp16).
+#include <cstdlib>
+#include <cooperative_groups.h>
 #include "ops.cuh"
 
+namespace cg = cooperative_groups;
+
 namespace etai {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Single-launch GroupNorm(+SiLU) for UNet-sized tensors: x is read ONCE and y written once.
+//   work unit   = (batch row b, block of GB consecutive groups) = a [HW x cw] slab of the NHWC tensor (cw = GB * C/G
+//                 channels, contiguous cw*sizeof(T) bytes per pixel row);
+//   cluster     = CS thread blocks split the slab's pixel rows; every CTA copies its rows into shared memory while it
+//                 accumulates per-channel sum / sum-of-squares, publishes its per-group partials (double) in its own
+//                 shared memory, and after one cluster barrier every CTA folds the CS partials of its cluster through
+//                 distributed shared memory in rank order (fixed order: run-to-run and batch invariant), then normalises
+//                 its rows straight out of shared memory.
+// The partition (GB, CS) is a function of (HW, C, dtype) only, never of the batch size.  Slabs that do not fit in the
+// cluster's shared memory re-read x from global/L2 in the apply pass ("resident = 0"); tensors too large for eight CTAs
+// per unit (VAE resolutions) keep the two-launch path below.  Roofline: HBM / L2 bandwidth, 2 * elements * sizeof bytes.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GNC_THREADS = 256, GNC_UNROLL = 8;
+
+struct GnCPlan {
+    bool ok = false;
+    int GB = 0, cw = 0, nv = 0, CS = 1, rows_per_cta = 0, resident = 0, RP = 0;
+    size_t smem = 0;
+};
+
+static GnCPlan gn_cluster_plan(long HW, int C, int G, size_t esz) {
+    GnCPlan best;
+    const int cpg = C / G;
+    const size_t tiers[3] = {48 * 1024, 96 * 1024, 200 * 1024};  // per-CTA slab budget: many CTAs / 2 per SM / 1 per SM
+    for (int strict = 1; strict >= 0 && !best.ok; --strict) {
+        for (int tier = 0; tier < 3 && !best.ok; ++tier) {
+            for (int GB = 1; GB <= G && !best.ok; GB *= 2) {
+                if (G % GB) continue;
+                const int cw = GB * cpg;
+                if (cw % 8 || cw / 8 > GNC_THREADS) continue;
+                if (cw * esz < 128 || (strict && (cw * esz) % 32)) continue;  // >= one line per row; whole 32-byte sectors
+                for (int CS = 1; CS <= 8; CS *= 2) {
+                    const long rows = (HW + CS - 1) / CS;
+                    if ((size_t)rows * cw * esz > tiers[tier]) continue;
+                    best.ok = true; best.GB = GB; best.cw = cw; best.nv = cw / 8; best.CS = CS;
+                    best.rows_per_cta = (int)rows; best.resident = 1;
+                    break;
+                }
+            }
+        }
+    }
+    if (!best.ok) {  // not resident: stats pass + apply pass both stream from global (the second read hits L2)
+        for (int GB = 1; GB <= G && !best.ok; GB *= 2) {
+            const int cw = GB * cpg;
+            if (G % GB || cw % 8 || cw / 8 > GNC_THREADS || (cw * esz) % 32 || cw * esz < 128) continue;
+            const long rows = (HW + 7) / 8;
+            if (rows > 1024) continue;  // too few CTAs per unit for a tensor this large: two-launch path
+            best.ok = true; best.GB = GB; best.cw = cw; best.nv = cw / 8; best.CS = 8; best.rows_per_cta = (int)rows;
+            best.resident = 0;
+        }
+    }
+    if (best.ok) {
+        best.RP = GNC_THREADS / best.nv;
+        size_t slab = best.resident ? (size_t)best.rows_per_cta * best.cw * esz : 0;
+        size_t red = (size_t)best.RP * best.cw * 2 * sizeof(float);
+        best.smem = ((slab + 15) & ~size_t(15)) + red + (size_t)best.GB * 2 * sizeof(double) + (size_t)best.GB * sizeof(float2) + 64;
+    }
+    return best;
+}
+
+template <typename T, bool SILU>
+__global__ void __launch_bounds__(GNC_THREADS) gn_cluster_k(const T* __restrict__ x, T* __restrict__ y,
+                                                            const T* __restrict__ gamma, const T* __restrict__ beta,
+                                                            long HW, int C, int cpg, int GB, int cw, int nv, int RP,
+                                                            int rows_per_cta, int resident, float eps) {
+    extern __shared__ __align__(32) unsigned char gsm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned CS = cluster.num_blocks(), rank = cluster.block_rank();
+    const int gblock = blockIdx.x / CS, b = blockIdx.y;
+    const int tid = threadIdx.x, v = tid % nv, rl = tid / nv;
+    const bool active = rl < RP;
+    const size_t slab_bytes = resident ? (((size_t)rows_per_cta * cw * sizeof(T) + 15) & ~size_t(15)) : 0;
+    T* slab = reinterpret_cast<T*>(gsm);
+    float* red = reinterpret_cast<float*>(gsm + slab_bytes);                    // [RP][2][cw]
+    double* part = reinterpret_cast<double*>(gsm + slab_bytes + (size_t)RP * cw * 2 * sizeof(float));  // [GB][2]
+    float2* stat = reinterpret_cast<float2*>(part + 2 * GB);                    // [GB] (mean, rstd)
+
+    const long r0 = (long)rank * rows_per_cta;
+    const long r1 = r0 + rows_per_cta < HW ? r0 + rows_per_cta : HW;
+    const long col = (long)gblock * cw + v * 8;
+    const T* xb = x + (long)b * HW * C + col;
+    T* yb = y + (long)b * HW * C + col;
+
+    // ---- pass 1: bring the rows in and accumulate per-channel partial sums in registers ----
+    float s[8], ss[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+    if (active && r1 > r0) {
+        if (resident) {
+            // Every 16-byte piece of this thread's rows is put in flight at once with cp.async (global -> shared, no
+            // register staging): ~80 KB outstanding per CTA.  With register-staged loads (4 x 16 B per thread per round
+            // trip) the kernel was latency-bound at 1.5 TB/s.  Each thread later reads back only what it copied itself, so
+            // cp.async.wait_all is the only synchronisation the slab needs.
+            for (long row = r0 + rl; row < r1; row += RP) {
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(slab + (row - r0) * cw + v * 8);
+                const T* src = xb + row * C;
+#pragma unroll
+                for (int q = 0; q < (int)(8 * sizeof(T) / 16); ++q)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * q),
+                                 "l"(reinterpret_cast<const char*>(src) + 16 * q) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            for (long row = r0 + rl; row < r1; row += RP) {
+                const Pack<T, 8> raw = *reinterpret_cast<const Pack<T, 8>*>(slab + (row - r0) * cw + v * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float t = to_f<T>(raw.v[j]);
+                    s[j] += t;
+                    ss[j] = fmaf(t, t, ss[j]);
+                }
+            }
+        } else {
+            for (long row = r0 + rl; row < r1; row += (long)RP * GNC_UNROLL) {
+                Pack<T, 8> raw[GNC_UNROLL];
+#pragma unroll
+                for (int u = 0; u < GNC_UNROLL; ++u) {  // branch-free loads (rows past the end re-read the last row, masked below)
+                    const long rr = row + (long)u * RP;
+                    raw[u] = *reinterpret_cast<const Pack<T, 8>*>(xb + (rr < r1 ? rr : r1 - 1) * C);
+                }
+#pragma unroll
+                for (int u = 0; u < GNC_UNROLL; ++u) {
+                    if (row + (long)u * RP < r1) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float t = to_f<T>(raw[u].v[j]);
+                            s[j] += t;
+                            ss[j] = fmaf(t, t, ss[j]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (active) {
+        float* S = red + (long)rl * 2 * cw + v * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { S[j] = s[j]; S[cw + j] = ss[j]; }
+    }
+    __syncthreads();
+    // fold the RP row lanes per channel (fixed order), then the channels of each group (double)
+    for (int c = tid; c < 2 * cw; c += GNC_THREADS) {
+        float a = red[c];
+        for (int r = 1; r < RP; ++r) a += red[(long)r * 2 * cw + c];
+        red[c] = a;
+    }
+    __syncthreads();
+    if (tid < GB) {
+        double a = 0.0, aa = 0.0;
+        for (int i = 0; i < cpg; ++i) {
+            a += (double)red[tid * cpg + i];
+            aa += (double)red[cw + tid * cpg + i];
+        }
+        part[2 * tid] = a;
+        part[2 * tid + 1] = aa;
+    }
+    cluster.sync();  // every CTA's partials are visible cluster-wide
+    if (tid < GB) {
+        double a = 0.0, aa = 0.0;
+        for (unsigned r = 0; r < CS; ++r) {  // rank order: deterministic
+            const double* rp = cluster.map_shared_rank(part, r);
+            a += rp[2 * tid];
+            aa += rp[2 * tid + 1];
+        }
+        const double n = (double)HW * cpg;
+        const double mean = a / n;
+        double var = aa / n - mean * mean;
+        if (var < 0) var = 0;
+        stat[tid] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+    cluster.sync();  // remote reads are done (a CTA may now run ahead and exit); also orders stat[] for this CTA
+    if (!active || r1 <= r0) return;
+    // ---- pass 2: normalise + affine (+SiLU) out of shared memory ----
+    float sc[8], sh[8];
+    {
+        float ga[8], be[8];
+        load8<T>(gamma + col, ga);
+        load8<T>(beta + col, be);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float2 st = stat[(v * 8 + j) / cpg];
+            sc[j] = st.y * ga[j];
+            sh[j] = be[j] - st.x * sc[j];
+        }
+    }
+    for (long row = r0 + rl; row < r1; row += (long)RP * GNC_UNROLL) {
+        Pack<T, 8> raw[GNC_UNROLL];
+#pragma unroll
+        for (int u = 0; u < GNC_UNROLL; ++u) {
+            const long rr = row + (long)u * RP;
+            const long rc = rr < r1 ? rr : r1 - 1;
+            raw[u] = resident ? *reinterpret_cast<const Pack<T, 8>*>(slab + (rc - r0) * cw + v * 8)
+                              : *reinterpret_cast<const Pack<T, 8>*>(xb + rc * C);
+        }
+#pragma unroll
+        for (int u = 0; u < GNC_UNROLL; ++u) {
+            const long rr = row + (long)u * RP;
+            if (rr < r1) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float t = fmaf(to_f<T>(raw[u].v[j]), sc[j], sh[j]);
+                    o[j] = SILU ? silu_for<T>(t) : t;
+                }
+                store8<T>(yb + rr * C, o);
+            }
+        }
+    }
+}
+
+template <typename T, bool SILU>
+static void gn_cluster_launch(const GnCPlan& p, const void* x, void* y, const void* gamma, const void* beta, int B, long HW,
+                              int C, int G, float eps, cudaStream_t s) {
+    static size_t configured = 0;  // largest dynamic shared-memory size this instantiation was opted in for
+    if (p.smem > configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(gn_cluster_k<T, SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+        configured = p.smem;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((G / p.GB) * p.CS), (unsigned)B, 1);
+    cfg.blockDim = dim3(GNC_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, gn_cluster_k<T, SILU>, (const T*)x, (T*)y, (const T*)gamma, (const T*)beta, HW, C,
+                                  C / G, p.GB, p.cw, p.nv, p.RP, p.rows_per_cta, p.resident, eps));
+}
+
+// returns false when the shape is left to the two-launch path
+static bool groupnorm_cluster(const void* x, void* y, const void* gamma, const void* beta, int B, long HW, int C, int G,
+                              float eps, bool silu, int dtype, cudaStream_t s) {
+    static const bool disabled = [] { const char* e = getenv("ETAI_GN_TWO_PASS"); return e && e[0] == '1'; }();
+    if (disabled || B > 65535) return false;
+    GnCPlan p = gn_cluster_plan(HW, C, G, dtype_size(dtype));
+    if (!p.ok) return false;
+    ETAI_DISPATCH_DTYPE(dtype, T, {
+        if (silu) gn_cluster_launch<T, true>(p, x, y, gamma, beta, B, HW, C, G, eps, s);
+        else gn_cluster_launch<T, false>(p, x, y, gamma, beta, B, HW, C, G, eps, s);
+    });
+    return true;
+}
+
+int groupnorm_launches(long HW, int C, int groups, int dtype) {
+    static const bool disabled = [] { const char* e = getenv("ETAI_GN_TWO_PASS"); return e && e[0] == '1'; }();
+    if (disabled || C % 8 || C % groups) return 2;
+    return gn_cluster_plan(HW, C, groups, dtype_size(dtype)).ok ? 1 : 2;
+}
 
 static constexpr int GN_MAX_CHUNKS = 256;
 
@@ -206,7 +465,7 @@ __global__ void __launch_bounds__(512, 2) gn_apply_k(const T* __restrict__ x, T*
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float t = fmaf(to_f<T>(raw[u].v[j]), sc[j], sh[j]);
-                o[j] = SILU ? silu_f(t) : t;
+                o[j] = SILU ? silu_for<T>(t) : t;
             }
             long rr = row + (long)u * R;
             if (rr < row1) store8<T>(yb + rr * C, o);
@@ -219,6 +478,7 @@ void groupnorm(const void* x, void* y, const void* gamma, const void* beta, int 
     ETAI_CHECK(C % 8 == 0 && C % groups == 0 && groups <= 64, ETAI_ERR_ARG, "groupnorm: C%8, C%groups, groups<=64");
     ETAI_CHECK(C / 8 <= 512, ETAI_ERR_ARG, "groupnorm: C too large");
     ETAI_CHECK(ws != nullptr, ETAI_ERR_ARG, "groupnorm: workspace required");
+    if (groupnorm_cluster(x, y, gamma, beta, B, HW, C, groups, eps, silu, dtype, s)) return;
     GnPlan p = gn_plan(HW, C);
     size_t smem = (size_t)2 * p.R * C * sizeof(float);
     if (smem < (size_t)p.threads * 2 * sizeof(double)) smem = (size_t)p.threads * 2 * sizeof(double);  // final-fold scratch

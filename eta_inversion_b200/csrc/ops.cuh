@@ -37,6 +37,7 @@ void skinny_linear(const float* x, const void* W, const void* bias, float* out, 
 // ---------------- normalisation ---------------------------------------------------------------
 size_t groupnorm_workspace_bytes(int B, long HW, int C, int groups);
 size_t groupnorm_ticket_offset(int B, int groups);  // byte offset of the B int tickets (must be zero before first use)
+int groupnorm_launches(long HW, int C, int groups, int dtype);  // 1 (single cluster launch) or 2 (stats + apply)
 void groupnorm(const void* x, void* y, const void* gamma, const void* beta, int B, long HW, int C, int groups,
                float eps, bool silu, int dtype, void* ws, cudaStream_t s);
 void layernorm(const void* x, void* y, const void* gamma, const void* beta, long M, int C, float eps, int dtype,

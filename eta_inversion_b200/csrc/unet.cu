@@ -319,7 +319,7 @@ struct etai_unet {
         if (arena.base) {
             cudaEvent_t e = prof_begin(s);
             groupnorm(x, y, n.g, n.b, B, HW, n.c, 32, eps, silu, dt, gn_ws, s);
-            prof_end(ETAI_PROF_GROUPNORM, e, 2, s);
+            prof_end(ETAI_PROF_GROUPNORM, e, groupnorm_launches(HW, n.c, 32, dt), s);
         }
         return y;
     }

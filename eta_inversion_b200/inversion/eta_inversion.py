@@ -84,6 +84,7 @@ class EtaInversion(DiffusionInversion):
         self.seed = seed if seed >= 0 else None
         self.noise_device = noise_device
         self.noise_provider = None  # optional callable(step_index) -> [K,1,4,64,64]; default = seeded generator
+        self.picks: list = []       # picked candidate index of every denoise step of the last loop (device tensors)
 
     # ---- noise -----------------------------------------------------------------------------------
     def sample_variance_noise(self, n: int, generator: Optional[torch.Generator] = None) -> torch.Tensor:
@@ -192,7 +193,8 @@ class EtaInversion(DiffusionInversion):
         n = latent.shape[0]
         losses = None
         if eta > 0 and cand.shape[0] > 1:
-            losses, _ = E.eta_noise_losses(eps_raw, latent, src_prev, a_t, a_p, g, eta, var, cand)
+            losses, best = E.eta_noise_losses(eps_raw, latent, src_prev, a_t, a_p, g, eta, var, cand)
+            self.picks.append(best)  # device int32 [1] per step, never read inside the loop (tests / diagnostics)
         eta_map = None
         delta_mask = None
         if self.mask_mode_cfg is not None:
@@ -223,6 +225,7 @@ class EtaInversion(DiffusionInversion):
             mask = F.interpolate(mask[None, None].float(), (64, 64), mode="bilinear")[0].to(self.model.device)
         steps = self.scheduler_bwd.timesteps
         noise = self._noise_for_loop(len(steps))
+        self.picks = []
         for i, t in enumerate(self.pbar(steps, desc="backward")):
             latent, noise_pred = self.predict_step_backward(
                 latent, t, context, source_latent_prev=inv_result["latents"][-(i + 2)], mask=mask,

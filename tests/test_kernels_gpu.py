@@ -86,16 +86,34 @@ def test_gemm_tc_large(dtype, M, N, K):
         assert _relerr(out[m].float(), ref[m]) < 4 * TOL[dtype]
 
 
-def test_gemm_tc_large_geglu():
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("M,N,K", [(65536, 320, 320), (32768 + 77, 960, 320), (16384, 640, 2560), (65536, 320, 1280),
+                                   (4096, 3840, 1280)])
+def test_gemm_tc_wide_tiles(dtype, M, N, K):
+    """Shapes the host routes to the 128 x 320 tile (two UMMAs of N = 160 per k-step, single-buffered accumulators)."""
+    from eta_inversion_b200 import engine as E
+    A, W = _rand((M, K), 1).to(dtype).cuda(), _rand((N, K), 2, K ** -0.5).to(dtype).cuda()
+    b, r = _rand((N,), 3).to(dtype).cuda(), _rand((M, N), 4).to(dtype).cuda()
+    out = E.gemm(A, W, b, r)
+    ref = torch.addmm(r.float(), A.float(), W.float().T) + b.float()
+    assert _relerr(out.float(), ref) < TOL[dtype]
+    for m in (0, 127, 128, M - 1):
+        assert _relerr(out[m].float(), ref[m]) < 4 * TOL[dtype]
+    for n0 in (0, 160, N - 160):  # every accumulator half of the first / last tile column
+        assert _relerr(out[:, n0:n0 + 160].float(), ref[:, n0:n0 + 160]) < 2 * TOL[dtype]
+
+
+@pytest.mark.parametrize("M,C", [(8192, 320), (65536, 320), (16384, 640)])
+def test_gemm_tc_large_geglu(M, C):
     from eta_inversion_b200 import engine as E
     dtype = torch.float16
-    M, C = 8192, 320
     A, W, b = _rand((M, C), 1).to(dtype).cuda(), _rand((8 * C, C), 2, C ** -0.5).to(dtype).cuda(), _rand((8 * C,), 3).to(dtype).cuda()
     Wi = torch.stack([W[:4 * C], W[4 * C:]], 1).reshape(8 * C, C).contiguous()
     bi = torch.stack([b[:4 * C], b[4 * C:]], 1).reshape(8 * C).contiguous()
     out = E.gemm(A, Wi, bi, geglu=True)
     h = A.float() @ W.float().T + b.float()
     ref = h[:, :4 * C] * F.gelu(h[:, 4 * C:])
+    del h
     assert _relerr(out.float(), ref) < TOL[dtype]
 
 
@@ -134,7 +152,8 @@ def test_conv3x3_tc(dtype, B, H, Ci, Co, stride):
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("B,H,Ci,Co", [(5, 64, 320, 320), (9, 32, 640, 640), (12, 16, 1280, 1280), (40, 8, 1280, 1280),
-                                        (11, 16, 2560, 1280)])
+                                        (11, 16, 2560, 1280), (16, 64, 320, 320), (16, 64, 960, 320), (16, 32, 1280, 640),
+                                        (16, 16, 2560, 1280), (16, 8, 2560, 1280)])
 def test_conv3x3_tc_large(dtype, B, H, Ci, Co):
     """Implicit-GEMM conv at co-batched sizes (odd image counts: the last 128-pixel box is partly out of range)."""
     from eta_inversion_b200 import engine as E
@@ -150,9 +169,13 @@ def test_conv3x3_tc_large(dtype, B, H, Ci, Co):
         assert _relerr(out[img].float(), ref[img]) < 4 * TOL[dtype]
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("B,HW,C,silu", [(2, 4096, 320, True), (1, 1024, 960, True), (3, 64, 2560, True), (2, 256, 1920, False),
-                                         (1, 4096, 640, False)])
+                                         (1, 4096, 640, False),
+                                         (2, 4096, 960, True),     # fp32: slab not resident (apply re-reads x); 16-bit: 1 CTA/SM
+                                         (2, 1024, 1280, True), (5, 256, 640, False), (3, 1024, 1920, True),
+                                         (2, 100, 320, True),      # rows not divisible by the cluster size
+                                         (1, 16384, 128, True)])   # VAE-sized: two-launch path
 def test_groupnorm(dtype, B, HW, C, silu):
     from eta_inversion_b200 import engine as E
     x = (_rand((B, HW, C), 1) * 2 + 0.5).to(dtype).cuda()
@@ -161,7 +184,20 @@ def test_groupnorm(dtype, B, HW, C, silu):
     ref = F.group_norm(x.float().permute(0, 2, 1), 32, g.float(), b.float(), 1e-5).permute(0, 2, 1)
     if silu:
         ref = F.silu(ref)
-    assert _relerr(out.float(), ref) < (2e-5 if dtype == torch.float32 else 2e-3)
+    assert _relerr(out.float(), ref) < {torch.float32: 2e-5, torch.float16: 2e-3, torch.bfloat16: 1.6e-2}[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_groupnorm_is_batch_invariant_and_deterministic(dtype):
+    """A row's result must not depend on what it is batched with (lock-step groups) nor vary run to run (A/B/A)."""
+    from eta_inversion_b200 import engine as E
+    HW, C = 1024, 640
+    x = (_rand((5, HW, C), 7) * 2 + 0.5).to(dtype).cuda()
+    g, b = (1 + 0.1 * _rand((C,), 2)).to(dtype).cuda(), (0.1 * _rand((C,), 3)).to(dtype).cuda()
+    full = E.groupnorm(x, g, b, 32, 1e-5, True)
+    assert torch.equal(full, E.groupnorm(x, g, b, 32, 1e-5, True))
+    for r in (0, 3):
+        assert torch.equal(full[r:r + 1], E.groupnorm(x[r:r + 1].contiguous(), g, b, 32, 1e-5, True))
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
@@ -279,3 +315,73 @@ def test_errors_are_loud():
     A = torch.zeros(8, 24, device="cuda", dtype=torch.float16)
     with pytest.raises(RuntimeError, match="tcgen05"):
         E.gemm(A, torch.zeros(8, 24, device="cuda", dtype=torch.float16))  # K not a multiple of 64
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# control-aware cross-attention (etai_cross_attention): the fused softmax -> prompt-to-prompt edit -> store -> PV of ONE
+# layer against the explicit computation of the reference (ptp_utils.py:238-253 + ptp.py:205-274), heads materialised.
+# ---------------------------------------------------------------------------------------------------------------------
+def _ref_cross_attention(q, k, v, heads, scale, pairs, mapper, blend_a, equalizer, alpha, store_rows):
+    B, N, C = q.shape
+    L, d = k.shape[1], C // heads
+    def split(t):
+        return t.float().reshape(t.shape[0], t.shape[1], heads, d).permute(0, 2, 1, 3)  # [B,h,n,d]
+    P = torch.softmax(split(q) @ split(k).transpose(-1, -2) * scale, dim=-1)            # [B,h,N,L]
+    for p, (br, tr) in enumerate(pairs or []):
+        base, tgt = P[br], P[tr]
+        rep = base @ mapper[p].float()                                                   # einsum('hpw,wn->hpn')
+        f = equalizer[p].float() * (blend_a[p].float() * rep + (1 - blend_a[p].float()) * tgt)
+        P[tr] = alpha[p].float() * f + (1 - alpha[p].float()) * tgt                      # no renormalisation
+    out = (P @ split(v)).permute(0, 2, 1, 3).reshape(B, N, C)
+    store = None if store_rows is None else torch.stack([P[r].sum(0) for r in store_rows])  # post-edit, summed over heads
+    return out, store
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("N,d,mode", [(256, 160, "replace"), (256, 160, "refine"), (1024, 80, "replace"), (4096, 40, "refine"),
+                                      (64, 160, "replace"), (256, 160, "none")])
+def test_cross_attention_control(dtype, N, d, mode):
+    from eta_inversion_b200 import engine as E
+    B, heads, L, X = 6, 8, 77, 768
+    C = heads * d
+    q = _rand((B, N, C), 1).to(dtype).cuda()
+    ld = 2 * C + 64                                     # K at column 32, V at column 32 + C of a wider buffer
+    kv = _rand((B, L, ld), 2).to(dtype).cuda()
+    koff, voff = 32, 32 + C
+    k, v = kv[:, :, koff:koff + C], kv[:, :, voff:voff + C]
+    scale = 2.5 * d ** -0.5                             # peaky rows: the edit must act on structured probabilities
+    pairs = None if mode == "none" else [(2, 3), (4, 5)]
+    gen = torch.Generator().manual_seed(5)
+    if mode == "replace":   # word-swap mapper: permutation-like with a few fractional rows (seq_aligner.get_replacement_mapper)
+        mapper = torch.stack([torch.eye(L)[torch.randperm(L, generator=gen)] for _ in range(2)])
+        mapper[:, 5, :] = 0
+        mapper[:, 5, 5:8] = 1 / 3
+        blend_a = torch.ones((2, L))
+    elif mode == "refine":  # gather by index + per-token blend (ptp.py:247-259): one-hot mapper, alphas in {0,1}
+        idx = torch.stack([torch.randperm(L, generator=gen) for _ in range(2)])
+        mapper = torch.zeros((2, L, L))
+        for p in range(2):
+            mapper[p, idx[p], torch.arange(L)] = 1.0
+        blend_a = (torch.rand((2, L), generator=gen) > 0.3).float()
+    else:
+        mapper = blend_a = None
+    if pairs:
+        equalizer = torch.ones((2, L))
+        equalizer[:, 2] = 2.0                           # reweight one word (ptp.py:262-274)
+        alpha = (torch.rand((2, L), generator=gen) > 0.25).float()
+        mapper, blend_a, equalizer, alpha = [t.cuda().contiguous() for t in (mapper, blend_a, equalizer, alpha)]
+    else:
+        equalizer = alpha = None
+    store_rows = [3, 2, 5, 0] if N <= 1024 else None
+    acc = torch.full((len(store_rows), N, L), 0.5, device="cuda") if store_rows else None  # accumulated in place
+    out = E.cross_attention(q, kv, heads, koff, voff, scale, pairs, mapper, blend_a, equalizer, alpha, store_rows, acc)
+    ref, ref_store = _ref_cross_attention(q, k, v, heads, scale, pairs, mapper, blend_a, equalizer, alpha, store_rows)
+    assert _relerr(out.float(), ref) < TOL[dtype]
+    if store_rows:
+        assert _relerr(acc - 0.5, ref_store) < TOL[dtype]
+    # the SIMT fp32-math path on the same 16-bit inputs agrees as well
+    if dtype != torch.float32:
+        acc2 = torch.zeros_like(acc) if store_rows else None
+        out2 = E.cross_attention(q, kv, heads, koff, voff, scale, pairs, mapper, blend_a, equalizer, alpha, store_rows, acc2,
+                                 math_mode=E.MATH_SIMT)
+        assert _relerr(out2.float(), ref) < TOL[dtype]
