@@ -22,6 +22,7 @@ from .inversion.ddpm_inversion import DDPMInversion
 from .inversion.edict_inversion import EdictInversion
 from .inversion.eta_inversion import EtaInversion
 from .inversion.negative_prompt_inversion import NegativePromptInversion
+from .inversion.null_text_inversion import NullTextInversion
 from .inversion.proximal_negative_prompt_inversion import ProximalNegativePromptInversion
 from .inversion.regularized_diffusion_inversion import RegularizedDiffusionInversion
 from .models import StablePostProc, StablePreprocess, load_diffusion_model  # noqa: F401
@@ -40,7 +41,7 @@ _inverters = {
     "npi": NegativePromptInversion,
     "dirinv": DirectInversion,
     "etainv": EtaInversion,
-    "nti": _out_of_scope("nti", "needs the UNet dgrad path"),
+    "nti": NullTextInversion,
     "proxnpi": ProximalNegativePromptInversion,
     "edict": EdictInversion,
     "ddpminv": DDPMInversion,

@@ -38,6 +38,17 @@ class EtaiUnetCfg(C.Structure):
                 ("max_batch", C.c_int32)]
 
 
+class EtaiVaeCfg(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("math_mode", C.c_int32), ("block_out_channels", C.c_int32 * 4),
+                ("image_hw", C.c_int32), ("max_batch", C.c_int32)]
+
+
+class EtaiClipCfg(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("math_mode", C.c_int32), ("vocab", C.c_int32), ("hidden", C.c_int32),
+                ("layers", C.c_int32), ("heads", C.c_int32), ("ffn", C.c_int32), ("max_len", C.c_int32),
+                ("max_batch", C.c_int32)]
+
+
 class EtaiAttnCtrl(C.Structure):
     _fields_ = [("flags", C.c_int32),
                 ("self_q_row", C.POINTER(C.c_int32)), ("self_k_row", C.POINTER(C.c_int32)),
@@ -59,9 +70,22 @@ SYMBOLS = {
     "etai_unet_clone": (C.c_int, [C.POINTER(_vp), _vp, _i32]),
     "etai_unet_set_context": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "etai_unet_forward": (C.c_int, [_vp, _vp, _f, _i32, _i32, C.POINTER(EtaiAttnCtrl), _vp, _vp]),
+    "etai_unet_enable_backward": (C.c_int, [_vp, _i32]),
+    "etai_unet_forward_train": (C.c_int, [_vp, _vp, _f, _i32, _i32, _vp, _vp]),
+    "etai_unet_backward_ctx": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "etai_unet_device_bytes": (_i64, [_vp]),
     "etai_unet_launch_count": (_i64, [_vp]),
     "etai_unet_profile": (C.c_int, [_vp, _i32, C.POINTER(C.c_float), C.POINTER(_i32)]),
+    "etai_vae_create": (C.c_int, [C.POINTER(_vp), C.POINTER(EtaiVaeCfg), C.POINTER(EtaiTensor), _i32, _i32]),
+    "etai_vae_destroy": (C.c_int, [_vp]),
+    "etai_vae_encode": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
+    "etai_vae_decode": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp]),
+    "etai_vae_launch_count": (_i64, [_vp]),
+    "etai_vae_device_bytes": (_i64, [_vp]),
+    "etai_clip_create": (C.c_int, [C.POINTER(_vp), C.POINTER(EtaiClipCfg), C.POINTER(EtaiTensor), _i32, _i32]),
+    "etai_clip_destroy": (C.c_int, [_vp]),
+    "etai_clip_encode": (C.c_int, [_vp, C.POINTER(_i32), _i32, _vp, _i32, _vp]),
+    "etai_clip_launch_count": (_i64, [_vp]),
     "etai_cfg_ddim_step": (C.c_int, [_vp, _i32, _i32, _f, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
     "etai_eta_noise_losses": (C.c_int, [_vp, _i32, _i32, _f, _vp, _vp, _f, _f, _f, _f, _vp, _i32, _i64, _vp, _vp, _vp]),
     "etai_groupnorm": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _f, _i32, _i32, _vp, _i64, _vp]),
@@ -99,6 +123,25 @@ def load() -> C.CDLL:
         raise RuntimeError(f"etai: ABI mismatch, library {lib.etai_abi_version()} vs binding {ABI_VERSION}")
     _lib = lib
     return lib
+
+
+def tensor_table(state_dict):
+    """state_dict -> (ctypes array of etai_tensor, keep-alive list): the weight table every *_create entry point takes."""
+    keep, arr = [], (EtaiTensor * len(state_dict))()
+    for i, (name, t) in enumerate(state_dict.items()):
+        t = t.detach()
+        if t.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            t = t.float()
+        t = t.contiguous()
+        keep.append(t)
+        arr[i].name = name.encode()
+        arr[i].data = t.data_ptr()
+        arr[i].dtype = dtype_code(t.dtype)
+        arr[i].ndim = t.ndim
+        for d in range(t.ndim):
+            arr[i].shape[d] = t.shape[d]
+        arr[i].on_device = 1 if t.is_cuda else 0
+    return arr, keep
 
 
 def check(rc: int) -> None:

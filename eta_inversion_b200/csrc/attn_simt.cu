@@ -112,11 +112,11 @@ __global__ void __launch_bounds__(ATHREADS) attn_simt_k(SelfAttnArgs a) {
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
             float mnew = fmaxf(mrow[i], mx);
-            float alpha = __expf(mrow[i] - mnew);  // exp(-inf) = 0 on the first tile
+            float alpha = expf(mrow[i] - mnew);  // exp(-inf) = 0 on the first tile
             float sum = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                float pv = __expf(s[i][j] - mnew);
+                float pv = expf(s[i][j] - mnew);
                 Ps[(i * 16 + ty) * PP + j * 8 + tx] = pv;
                 sum += pv;
             }

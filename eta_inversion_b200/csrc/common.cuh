@@ -94,7 +94,7 @@ __device__ __forceinline__ void store4(T* p, const float (&in)[4]) {
     *reinterpret_cast<Pack<T, 4>*>(p) = v;
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }  // fp32 parity path: accurate exp
 // SiLU for 16-bit outputs: x*sigmoid(x) = h + h*tanh(h), h = x/2 -- one MUFU op and two FMA-pipe ops instead of
 // ex2 + a full-precision division (~20 instructions); tanh.approx.f32 has a relative error of 2^-11, the size of the
 // fp16 output rounding.  The normalisation kernels are issue/MUFU-bound on B200 with the exact form (HBM delivers a 16-bit

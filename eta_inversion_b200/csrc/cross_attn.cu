@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(CTHREADS) cross_attn_k(CrossAttnArgs a) {
                 float sum = 0.f;
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    p[j] = (lane + 32 * j < L) ? __expf(p[j] - mx) : 0.f;
+                    p[j] = (lane + 32 * j < L) ? expf(p[j] - mx) : 0.f;
                     sum += p[j];
                 }
                 float inv = 1.f / warp_sum(sum);

@@ -104,8 +104,8 @@ void upsample2x(const void* in, void* out, int B, int H, int W, int C, int dtype
 }
 
 template <typename T>
-__global__ void im2col3x3_k(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C, int stride, int Ho,
-                            int Wo, long total) {
+__global__ void im2col3x3_k(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C, int stride, int pad,
+                            int Ho, int Wo, long total) {
     constexpr int V = 16 / sizeof(T);
     int Cv = C / V;
     long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
@@ -116,19 +116,19 @@ __global__ void im2col3x3_k(const T* __restrict__ in, T* __restrict__ out, int H
     long m = r / 9;
     int ox = (int)(m % Wo), oy = (int)((m / Wo) % Ho);
     long b = m / ((long)Wo * Ho);
-    int iy = oy * stride + tap / 3 - 1, ix = ox * stride + tap % 3 - 1;
+    int iy = oy * stride + tap / 3 - pad, ix = ox * stride + tap % 3 - pad;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (iy >= 0 && iy < H && ix >= 0 && ix < W)
         v = reinterpret_cast<const uint4*>(in + ((b * H + iy) * W + ix) * (long)C)[cv];
     reinterpret_cast<uint4*>(out)[i] = v;
 }
-void im2col3x3(const void* in, void* out, int B, int H, int W, int C, int stride, int Ho, int Wo, int dtype,
+void im2col3x3(const void* in, void* out, int B, int H, int W, int C, int stride, int pad, int Ho, int Wo, int dtype,
                cudaStream_t s) {
     ETAI_DISPATCH_DTYPE(dtype, T, {
         constexpr int V = 16 / sizeof(T);
         ETAI_CHECK(C % V == 0, ETAI_ERR_ARG, "im2col: C must be a multiple of 16 bytes");
         long total = (long)B * Ho * Wo * 9 * (C / V);
-        im2col3x3_k<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)in, (T*)out, H, W, C, stride, Ho, Wo, total);
+        im2col3x3_k<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)in, (T*)out, H, W, C, stride, pad, Ho, Wo, total);
     });
     KERNEL_CHECK();
 }

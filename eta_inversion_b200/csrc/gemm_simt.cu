@@ -23,7 +23,7 @@ struct Params {
     int N, K;
     long lda, ldc, ldr, ldrb, rows_per_group;
     int geglu;
-    int H, Wd, Cin, stride, Ho, Wo;
+    int H, Wd, Cin, stride, Ho, Wo, pad;
 };
 
 // A-tile loader: each thread owns row (tid/2) and 8 consecutive k at (tid%2)*8
@@ -46,12 +46,12 @@ __device__ __forceinline__ void load_a(const Params& p, long m0, int k0, int tid
         long b = m / ((long)p.Wo * p.Ho);
         if ((p.Cin % 8) == 0) {
             int tap = k / p.Cin, c = k % p.Cin;
-            int iy = oy * p.stride + tap / 3 - 1, ix = ox * p.stride + tap % 3 - 1;
+            int iy = oy * p.stride + tap / 3 - p.pad, ix = ox * p.stride + tap % 3 - p.pad;
             if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.Wd) load8<T>(A + ((b * p.H + iy) * p.Wd + ix) * (long)p.Cin + c, v);
         } else {
             for (int j = 0; j < 8 && k + j < p.K; ++j) {
                 int kk = k + j, tap = kk / p.Cin, c = kk % p.Cin;
-                int iy = oy * p.stride + tap / 3 - 1, ix = ox * p.stride + tap % 3 - 1;
+                int iy = oy * p.stride + tap / 3 - p.pad, ix = ox * p.stride + tap % 3 - p.pad;
                 if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.Wd)
                     v[j] = to_f<T>(A[((b * p.H + iy) * p.Wd + ix) * (long)p.Cin + c]);
             }
@@ -186,7 +186,7 @@ void gemm_simt(const GemmArgs& a, cudaStream_t s) {
     p.lda = a.lda; p.ldc = a.ldc; p.ldr = a.ldr; p.ldrb = a.ldrb;
     p.rows_per_group = a.rows_per_group > 0 ? a.rows_per_group : 1;
     p.geglu = a.geglu;
-    p.H = a.H; p.Wd = a.Wd; p.Cin = a.Cin; p.stride = a.stride; p.Ho = a.Ho; p.Wo = a.Wo;
+    p.H = a.H; p.Wd = a.Wd; p.Cin = a.Cin; p.stride = a.stride; p.Ho = a.Ho; p.Wo = a.Wo; p.pad = a.pad;
     dim3 grid(cdiv(a.N, BN), cdiv(a.M, BM));
     ETAI_DISPATCH_DTYPE(a.dtype, T, {
         if (a.conv) gemm_simt_k<T, true><<<grid, THREADS, 0, s>>>(p);

@@ -199,11 +199,12 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const int tile = item % (p.tiles_m * p.tiles_n), split = item / (p.tiles_m * p.tiles_n);
                 const int n0 = (tile % p.tiles_n) * BN;
                 const long m0 = (long)(tile / p.tiles_n) * BM;
-                int b0 = 0, oy0 = 0;
+                int b0 = 0, oy0 = 0, ox0 = 0;
                 if (CONV) {
                     long hw = (long)p.Himg * p.Wimg;
                     b0 = (int)(m0 / hw);
                     oy0 = (int)((m0 % hw) / p.Wimg);
+                    ox0 = (int)((m0 % hw) % p.Wimg);  // non-zero only for images wider than one tile (VAE: 256, 512)
                 }
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = kb0 + p.kb_per_split < p.num_kb ? kb0 + p.kb_per_split : p.num_kb;
@@ -218,7 +219,7 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     unsigned char* sb = sa + S::A_BYTES;
                     if (CONV) {
                         int tap = kb / p.cin_blocks, cb = kb % p.cin_blocks;
-                        tma_load_4d(sa, &tmA, &full[s], cb * BK, tap % 3 - 1, oy0 + tap / 3 - 1, b0);
+                        tma_load_4d(sa, &tmA, &full[s], cb * BK, ox0 + tap % 3 - 1, oy0 + tap / 3 - 1, b0);
                     } else {
                         tma_load_2d(sa, &tmA, &full[s], kb * BK, (int)m0);
                     }
@@ -607,7 +608,9 @@ bool gemm_tc_supported(const GemmArgs& a) {
         if (a.Cin % 64 != 0) return false;
         if (a.stride == 1) {
             int W = a.Wd, H = a.H;
-            if (W > 128 || 128 % W != 0) return false;
+            if (a.pad != 1) return false;
+            if (W > 128) return W % 128 == 0;  // one tile = 128 consecutive pixels of one image row
+            if (128 % W != 0) return false;
             int bh = 128 / W < H ? 128 / W : H;
             if (H % bh != 0) return false;
             return true;
@@ -625,7 +628,7 @@ void gemm_tc(const GemmArgs& a0, void* ws, size_t ws_bytes, cudaStream_t s) {
         // the three downsample convs (0.7% of UNet FLOPs): gather to [M, 9*Cin] once, then a dense GEMM
         size_t need = (size_t)a.M * 9 * a.Cin * 2;
         ETAI_CHECK(ws && ws_bytes >= need, ETAI_ERR_ARG, "gemm_tc: stride-2 conv needs an im2col workspace");
-        im2col3x3(a.A, ws, a.B, a.H, a.Wd, a.Cin, 2, a.Ho, a.Wo, a.dtype, s);
+        im2col3x3(a.A, ws, a.B, a.H, a.Wd, a.Cin, 2, a.pad, a.Ho, a.Wo, a.dtype, s);
         a.A = ws; a.conv = 0; a.lda = 9L * a.Cin; a.K = 9 * a.Cin;
         ws_used = (need + 255) & ~size_t(255);
     }
@@ -664,7 +667,7 @@ void gemm_tc(const GemmArgs& a0, void* ws, size_t ws_bytes, cudaStream_t s) {
     }
     if (a.conv) {
         int W = a.Wd, H = a.H;
-        int bw = W, bh = 128 / W < H ? 128 / W : H, bb = 128 / (bw * bh);
+        int bw = W < 128 ? W : 128, bh = W >= 128 ? 1 : (128 / W < H ? 128 / W : H), bb = 128 / (bw * bh);
         uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)W, (uint64_t)H, (uint64_t)a.B};
         uint64_t str[3] = {(uint64_t)a.Cin * 2, (uint64_t)a.Cin * 2 * W, (uint64_t)a.Cin * 2 * W * H};
         uint32_t box[4] = {(uint32_t)BK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};

@@ -21,6 +21,7 @@ struct GemmArgs {
     int geglu = 0;
     // conv geometry (conv != 0)
     int conv = 0, B = 0, H = 0, Wd = 0, Cin = 0, stride = 1, Ho = 0, Wo = 0;
+    int pad = 1;  // leading zero padding (1 = symmetric pad-1 conv; 0 with stride 2 = the VAE's (0,1,0,1) asymmetric pad)
     int dtype = ETAI_F32;
 };
 
@@ -95,7 +96,7 @@ void nhwc_to_nchw(const void* in, int in_dtype, void* out, int out_dtype, int B,
 void convert(const void* in, int in_dtype, void* out, int out_dtype, long n, cudaStream_t s);
 void concat_channels(const void* a, int Ca, const void* b, int Cb, void* out, long rows, int dtype, cudaStream_t s);
 void upsample2x(const void* in, void* out, int B, int H, int W, int C, int dtype, cudaStream_t s);
-void im2col3x3(const void* in, void* out, int B, int H, int W, int C, int stride, int Ho, int Wo, int dtype,
+void im2col3x3(const void* in, void* out, int B, int H, int W, int C, int stride, int pad, int Ho, int Wo, int dtype,
                cudaStream_t s);
 void copy_rows(void* base, long row_elems, int src_row, int n_src, int dst_row, int n_dst, int dtype, cudaStream_t s);
 void timestep_sincos(const float* t_dev, float* out, int dim, cudaStream_t s);
@@ -104,6 +105,51 @@ void add_inplace(void* y, const void* x, long n, int dtype, cudaStream_t s);
 // weight repack: OIHW -> O,(ky,kx),I ; optional GEGLU row interleave
 void pack_conv_weight(const float* oihw, void* out, int O, int I, int Opad, int Ipad, int dtype, cudaStream_t s);
 void pack_geglu_weight(const float* w, const float* b, void* wout, void* bout, int N2, int K, int dtype, cudaStream_t s);
+
+// ---------------- VAE / CLIP text tower only (textvae_ops.cu) -----------------------------------
+void softmax_rows(void* x, long rows, int n, float scale, int dtype, cudaStream_t s);  // in place, softmax(scale*x) per row
+void clip_embed(const int* ids, const void* tok, const void* pos, void* out, long rows, int L, int C, int vocab, int dtype,
+                cudaStream_t s);
+void quick_gelu(void* x, long n, int dtype, cudaStream_t s);                            // in place, x*sigmoid(1.702x)
+void clip_attention(const void* qkv, void* out, int B, int L, int heads, int d, float scale, int dtype, cudaStream_t s);
+
+// ---------------- backward (dgrad only; null-text inversion) -- backward.cu -----------------------
+void transpose_2d(const void* in, void* out, int R, int Cc, int dtype, cudaStream_t s);          // [R,Cc] -> [Cc,R]
+void conv_weight_flip(const void* in, void* out, int O, int I, int dtype, cudaStream_t s);       // [O,3,3,I] -> [I,3,3,O], taps mirrored
+void zero_stuff2x(const void* in, void* out, int B, int Ho, int Wo, int C, int dtype, cudaStream_t s);
+void upsample2x_bwd(const void* dout, void* din, int B, int H, int W, int C, int dtype, cudaStream_t s);
+void slice_cols(const void* in, long ld, int off, int C, void* out, bool accumulate, long rows, int dtype, cudaStream_t s);
+void scale_by_device_scalar(const void* in, void* out, const float* s_dev, bool invert, long n, int dtype, cudaStream_t s);
+void absmax_scale(const float* x, long n, float target, float* s_dev, cudaStream_t s);
+void geglu_fwd(const void* u, void* y, long M, int F, int dtype, cudaStream_t s);
+void geglu_bwd(const void* u, const void* dy, void* du, long M, int F, int dtype, cudaStream_t s);
+void groupnorm_bwd(const void* x, const void* dy, const void* gamma, const void* beta, void* dx, int B, long HW, int C,
+                   int groups, float eps, bool silu, int dtype, cudaStream_t s);
+void layernorm_bwd(const void* x, const void* dy, const void* gamma, void* dx, long M, int C, float eps, int dtype,
+                   cudaStream_t s);
+struct SelfAttnBwdArgs {
+    const void *q, *k, *v, *o, *dout;
+    void *dq, *dk, *dv;
+    float *lse, *dsum;  // [B,heads,N] scratch
+    int B, N, heads, d;
+    long ldq, ldk, ldv, ldo, lddo, lddq, lddk, lddv;
+    float scale;
+    int dtype;
+};
+void attention_bwd(const SelfAttnBwdArgs& a, cudaStream_t s);
+struct CrossAttnBwdArgs {
+    const void *q, *kv, *dout;
+    void* dq;      // [B,N,lddq] or null
+    float* part;   // scratch, cross_attention_bwd_partial_bytes()
+    float* dkv;    // [B*L, ld_dkv] fp32: columns [kv_off, kv_off+C) = dK, [kv_off+C, kv_off+2C) = dV (overwritten)
+    int B, N, L, heads, d;
+    long ldq, ldkv, lddo, lddq, ld_dkv;
+    int koff, voff, kv_off;
+    float scale;
+    int dtype;
+};
+size_t cross_attention_bwd_partial_bytes(int B, int N, int L, int C, int d);
+void cross_attention_bwd(const CrossAttnBwdArgs& a, cudaStream_t s);
 
 // ---------------- scheduler -------------------------------------------------------------------
 void cfg_ddim_step(const float* eps, int n, int has_cfg, float guidance, const float* x, float* x_out,

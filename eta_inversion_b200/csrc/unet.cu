@@ -6,23 +6,13 @@
 //   conv OIHW -> [O][ky][kx][I] (implicit-GEMM K order), to_q/to_k/to_v of attn1 stacked to one [3C,C] GEMM,
 //   all 16 cross-attention to_k/to_v stacked to one [sum 2C, 768] GEMM that runs once per context,
 //   all 22 time_emb_proj stacked to one skinny GEMM, GEGLU rows interleaved (value,gate) for the fused epilogue.
-#include <memory>
-#include <unordered_map>
-#include <vector>
-#include <string>
-#include <cstring>
-#include <cmath>
-#include <cstdlib>
-
-#include "ops.cuh"
+#include <unordered_set>
+#include "engine_base.cuh"
 
 namespace etai {
 
 namespace {
 
-struct Conv { void* w = nullptr; void* b = nullptr; int cin = 0, cout = 0; };
-struct Lin { void* w = nullptr; void* b = nullptr; int n = 0, k = 0; };
-struct Norm { void* g = nullptr; void* b = nullptr; int c = 0; };
 struct Res { Norm n1, n2; Conv c1, c2; Lin sc; bool has_sc = false; int cin = 0, cout = 0, temb_off = 0; };
 struct Tfm {
     Norm gn, ln1, ln2, ln3;
@@ -33,45 +23,14 @@ struct Tfm {
 // fp32 scratch layout of the time-embedding path
 constexpr int TB_SIN = 0, TB_H1 = 4096, TB_ST = 8192, TB_PROJ = 16384;
 
-// Packed device weights, shared (read-only) between a handle and its clones.
-struct WeightStore {
-    std::vector<void*> owned;
-    size_t bytes = 0;
-    int device = 0;
-    ~WeightStore() {
-        cudaSetDevice(device);
-        for (void* p : owned) cudaFree(p);
-    }
-};
-
-struct Arena {
-    char* base = nullptr;
-    size_t cap = 0, off = 0, peak = 0;
-    void* alloc(size_t bytes) {
-        size_t a = (off + 255) & ~size_t(255);
-        off = a + bytes;
-        if (off > peak) peak = off;
-        if (base == nullptr) return reinterpret_cast<void*>(size_t(256));  // planning pass: never dereferenced
-        ETAI_CHECK(off <= cap, ETAI_ERR_NOMEM, "activation arena exhausted");
-        return base + a;
-    }
-    void reset() { off = 0; }
-};
-
 }  // namespace
 
 }  // namespace etai
 
 using namespace etai;
 
-struct etai_unet {
+struct etai_unet : etai::OpCtx {
     etai_unet_cfg cfg;
-    int device = 0;
-    int dt = ETAI_F32;   // storage dtype
-    bool tc = false;     // tcgen05 path enabled
-    size_t esz = 4;
-    std::shared_ptr<WeightStore> wstore;  // device allocations of the packed weights (shared with clones)
-    size_t weight_bytes = 0;
 
     Conv conv_in, conv_out;
     Norm norm_out;
@@ -85,14 +44,10 @@ struct etai_unet {
     int n_tf = 0, temb_total = 0, kv_total = 0;
 
     // per-forward workspace
-    Arena arena;
     void* kv_cache = nullptr;  // [max_batch*ctx_len, kv_total]
     void* ctx_buf = nullptr;   // [max_batch*ctx_len, cross_dim] in storage dtype
     int ctx_rows = 0;          // batch rows of the cached context (0 = none)
     float* tbuf = nullptr;     // time embedding scratch (fp32)
-    void* gn_ws = nullptr;
-    void* tc_ws = nullptr;
-    size_t tc_ws_bytes = 0;
     // ---- CUDA-graph replay: all per-call inputs are staged into engine-owned buffers (stable addresses), the kernel
     // schedule of one forward is captured once per (batch, control structure) key and replayed afterwards.
     cudaStream_t gs = nullptr;          // engine stream (capture on the legacy default stream is not allowed)
@@ -111,114 +66,6 @@ struct etai_unet {
     bool map16_ready = false;
     size_t workspace_bytes = 0;
 
-    // ---- instrumentation: launch counter (always) + per-category CUDA-event timing (opt-in) -----
-    int64_t launches = 0;
-    bool prof_on = false;
-    struct ProfRec { int cat; cudaEvent_t a, b; };
-    std::vector<ProfRec> prof_recs;
-    cudaEvent_t prof_begin(cudaStream_t s) {
-        if (!prof_on || !arena.base) return nullptr;
-        cudaEvent_t e;
-        CUDA_CHECK(cudaEventCreate(&e));
-        CUDA_CHECK(cudaEventRecord(e, s));
-        return e;
-    }
-    void prof_end(int cat, cudaEvent_t a, int n_launches, cudaStream_t s) {
-        if (arena.base) launches += n_launches;
-        if (!a) return;
-        cudaEvent_t b;
-        CUDA_CHECK(cudaEventCreate(&b));
-        CUDA_CHECK(cudaEventRecord(b, s));
-        prof_recs.push_back({cat, a, b});
-    }
-
-    // ---- weight loading helpers -------------------------------------------------------------
-    std::unordered_map<std::string, const etai_tensor*> table;
-    float* stage = nullptr;
-    size_t stage_elems = 0;
-
-    void* dmalloc(size_t bytes) {
-        void* p = nullptr;
-        CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 256));
-        wstore->owned.push_back(p);
-        wstore->bytes += bytes;
-        weight_bytes += bytes;
-        return p;
-    }
-    const etai_tensor& find(const std::string& name) {
-        auto it = table.find(name);
-        ETAI_CHECK(it != table.end(), ETAI_ERR_ARG, ("missing weight: " + name).c_str());
-        return *it->second;
-    }
-    static size_t numel(const etai_tensor& t) {
-        size_t n = 1;
-        for (int i = 0; i < t.ndim; ++i) n *= (size_t)t.shape[i];
-        return n;
-    }
-    // fp32 copy of a named tensor in the staging buffer (device); valid until the next call
-    const float* staged(const std::string& name, std::initializer_list<int64_t> shape) {
-        const etai_tensor& t = find(name);
-        ETAI_CHECK(t.ndim == (int)shape.size(), ETAI_ERR_ARG, ("bad rank for " + name).c_str());
-        int i = 0;
-        for (int64_t s : shape) {
-            ETAI_CHECK(t.shape[i] == s, ETAI_ERR_ARG, ("bad shape for " + name).c_str());
-            ++i;
-        }
-        size_t n = numel(t);
-        ETAI_CHECK(n <= stage_elems, ETAI_ERR_ARG, "staging buffer too small");
-        if (t.dtype == ETAI_F32) {
-            CUDA_CHECK(cudaMemcpy(stage, t.data, n * 4, t.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
-        } else {
-            void* tmp = reinterpret_cast<char*>(stage) + stage_elems * 4;  // second half of the staging area
-            CUDA_CHECK(cudaMemcpy(tmp, t.data, n * 2, t.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
-            convert(tmp, t.dtype, stage, ETAI_F32, (long)n, 0);
-            CUDA_CHECK(cudaStreamSynchronize(0));
-        }
-        return stage;
-    }
-    // plain tensor converted to storage dtype at dst (device)
-    void put(const std::string& name, std::initializer_list<int64_t> shape, void* dst) {
-        const float* s = staged(name, shape);
-        size_t n = numel(find(name));
-        convert(s, ETAI_F32, dst, dt, (long)n, 0);
-        CUDA_CHECK(cudaStreamSynchronize(0));
-    }
-    Norm load_norm(const std::string& p, int c) {
-        Norm n;
-        n.c = c;
-        n.g = dmalloc(c * esz);
-        n.b = dmalloc(c * esz);
-        put(p + ".weight", {c}, n.g);
-        put(p + ".bias", {c}, n.b);
-        return n;
-    }
-    Lin load_lin(const std::string& p, int n, int k, bool bias, bool conv1x1 = false) {
-        Lin l;
-        l.n = n; l.k = k;
-        l.w = dmalloc((size_t)n * k * esz);
-        if (conv1x1) put(p + ".weight", {n, k, 1, 1}, l.w);
-        else put(p + ".weight", {n, k}, l.w);
-        if (bias) {
-            l.b = dmalloc(n * esz);
-            put(p + ".bias", {n}, l.b);
-        }
-        return l;
-    }
-    // cin_pad / cout_pad > 0: zero-pad to a tcgen05-friendly shape (conv_in 4 -> 64 input channels = one K block,
-    // conv_out 4 -> 32 output channels); the Conv then describes the padded problem.
-    Conv load_conv(const std::string& p, int cin, int cout, int cin_pad = 0, int cout_pad = 0) {
-        Conv c;
-        c.cin = cin_pad > 0 ? cin_pad : cin;
-        c.cout = cout_pad > 0 ? cout_pad : cout;
-        c.w = dmalloc((size_t)c.cout * 9 * c.cin * esz);
-        c.b = dmalloc(c.cout * esz);
-        CUDA_CHECK(cudaMemset(c.b, 0, c.cout * esz));
-        const float* s = staged(p + ".weight", {cout, cin, 3, 3});
-        pack_conv_weight(s, c.w, cout, cin, c.cout, c.cin, dt, 0);
-        CUDA_CHECK(cudaStreamSynchronize(0));
-        put(p + ".bias", {cout}, c.b);
-        return c;
-    }
     Res load_res(const std::string& p, int cin, int cout, int temb) {
         Res r;
         r.cin = cin; r.cout = cout;
@@ -276,62 +123,33 @@ struct etai_unet {
         return t;
     }
 
+    // ---- backward w.r.t. the text context (null-text inversion) ----
+    bool bwd_enabled = false;
+    int bwd_batch = 0;            // rows of the recorded train-mode forward (0 = none)
+    int bwd_max_batch = 0;
+    void* last_out = nullptr;     // conv_out result of the last forward (NHWC, padded channels)
+    std::unordered_map<const void*, void*> wT;   // packed forward weight -> dgrad weight (W^T / flipped conv filter)
+    std::vector<void*> bwd_owned;
+    Arena garena;                 // gradients + temporaries of one backward pass
+    float* dkv = nullptr;         // [bwd_max_batch*ctx_len, kv_total] fp32: d(K|V) of all 16 cross-attention layers
+    float* cross_part = nullptr;  // per-tile dK/dV partials of one cross-attention layer
+    float* lse_buf = nullptr;     // [2][bwd_max_batch*heads*HW] log-sum-exp and rowsum(dO*O) of one self-attention layer
+    float* scale_dev = nullptr;   // loss scale of the 16-bit backward pass (device scalar)
+    void* bwd_seed = nullptr;     // dL/d(conv_out result), NHWC
+    void* bwd_dctx = nullptr;     // result of the last walk: dL/d(ctx) in storage dtype
+    size_t cross_part_need = 0;
+    void enable_backward(int max_batch);
+    void* make_wT(const void* w, int n, int k, bool conv);
+    void backward_walk(int B, cudaStream_t s);
+    void backward_ctx(const float* d_eps, int B, float* d_ctx, cudaStream_t user);
+
     void build(const etai_tensor* weights, int n_weights);
     void plan_workspace();
     void set_context(const void* ctx, int io_dtype, int B, cudaStream_t s);
     void forward(const void* latent, float t, int io_dtype, int B, const etai_attn_ctrl* ctrl, void* eps_out,
-                 cudaStream_t s);
+                 cudaStream_t s, bool train = false);
     void run_body(int io_dtype, int B, const etai_attn_ctrl* ctrl, cudaStream_t s);
 
-    // ---- op wrappers --------------------------------------------------------------------------
-    void gemm(GemmArgs& a, cudaStream_t s) {
-        a.dtype = dt;
-        cudaEvent_t e = prof_begin(s);
-        bool use_tc = tc && gemm_tc_supported(a);
-        if (use_tc) gemm_tc(a, tc_ws, tc_ws_bytes, s);
-        else gemm_simt(a, s);
-        prof_end(a.conv ? ETAI_PROF_CONV : ETAI_PROF_GEMM, e, (use_tc && a.conv && a.stride == 2) ? 2 : 1, s);
-    }
-    void* linear(const void* x, long M, const Lin& l, const void* residual, cudaStream_t s, int geglu = 0) {
-        int nout = geglu ? l.n / 2 : l.n;
-        void* y = arena.alloc((size_t)M * nout * esz);
-        GemmArgs a;
-        a.A = x; a.W = l.w; a.C = y; a.bias = l.b; a.residual = residual;
-        a.M = M; a.N = l.n; a.K = l.k; a.lda = l.k; a.ldc = nout; a.ldr = nout; a.geglu = geglu;
-        if (arena.base) gemm(a, s);
-        return y;
-    }
-    void* conv3x3(const void* x, int B, int H, int W, const Conv& c, int stride, const float* rowbias,
-                  const void* residual, cudaStream_t s) {
-        int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-        long M = (long)B * Ho * Wo;
-        void* y = arena.alloc((size_t)M * c.cout * esz);
-        GemmArgs a;
-        a.A = x; a.W = c.w; a.C = y; a.bias = c.b; a.residual = residual; a.rowbias = rowbias;
-        a.rows_per_group = M; a.ldrb = 0;
-        a.M = M; a.N = c.cout; a.K = 9 * c.cin; a.ldc = c.cout; a.ldr = c.cout;
-        a.conv = 1; a.B = B; a.H = H; a.Wd = W; a.Cin = c.cin; a.stride = stride; a.Ho = Ho; a.Wo = Wo;
-        if (arena.base) gemm(a, s);
-        return y;
-    }
-    void* gnorm(const void* x, int B, long HW, const Norm& n, float eps, bool silu, cudaStream_t s) {
-        void* y = arena.alloc((size_t)B * HW * n.c * esz);
-        if (arena.base) {
-            cudaEvent_t e = prof_begin(s);
-            groupnorm(x, y, n.g, n.b, B, HW, n.c, 32, eps, silu, dt, gn_ws, s);
-            prof_end(ETAI_PROF_GROUPNORM, e, groupnorm_launches(HW, n.c, 32, dt), s);
-        }
-        return y;
-    }
-    void* lnorm(const void* x, long M, const Norm& n, cudaStream_t s) {
-        void* y = arena.alloc((size_t)M * n.c * esz);
-        if (arena.base) {
-            cudaEvent_t e = prof_begin(s);
-            layernorm(x, y, n.g, n.b, M, n.c, 1e-5f, dt, s);
-            prof_end(ETAI_PROF_LAYERNORM, e, 1, s);
-        }
-        return y;
-    }
     void* resnet(const void* x, int B, int H, int W, const Res& r, const etai_attn_ctrl* ctrl, bool inject_here,
                  cudaStream_t s) {
         long HW = (long)H * W, M = B * HW;
@@ -454,6 +272,12 @@ void* etai_unet::transformer(const void* x, int B, int H, int W, const Tfm& t, c
         else attention_simt(a, s);
         prof_end(ETAI_PROF_SELF_ATTN, e, 1, s);
     }
+    if (tape_on) {
+        ETAI_CHECK(!ctrl, ETAI_ERR_UNSUPPORTED, "train-mode forward does not take an attention control");
+        TapeRec r{T_SELF_ATTN, GemmArgs(), qkv, nullptr, ao};
+        r.B = B; r.HW = HW; r.heads = heads; r.d = d; r.C = C; r.scale = scale;
+        tape.push_back(r);
+    }
     h = linear(ao, M, t.o1, h, s);
     // ---- cross attention ----
     void* n2 = lnorm(h, M, t.ln2, s);
@@ -500,6 +324,11 @@ void* etai_unet::transformer(const void* x, int B, int H, int W, const Tfm& t, c
         if (tc && cross_attention_tc_supported(a)) nl = cross_attention_tc(a, s);
         else cross_attention(a, s);
         prof_end(ETAI_PROF_CROSS_ATTN, e, nl, s);
+    }
+    if (tape_on) {
+        TapeRec r{T_CROSS_ATTN, GemmArgs(), q2, nullptr, co};
+        r.B = B; r.HW = HW; r.heads = heads; r.d = d; r.C = C; r.scale = scale; r.kv_off = t.kv_off;
+        tape.push_back(r);
     }
     h = linear(co, M, t.o2, h, s);
     // ---- feed forward (GEGLU) ----
@@ -598,6 +427,11 @@ void etai_unet::run_body(int io_dtype, int B, const etai_attn_ctrl* ctrl, cudaSt
                 concat_channels(h, hc, sk.p, sk.C, cat, rows, dt, s);
                 prof_end(ETAI_PROF_OTHER, e, 1, s);
             }
+            if (tape_on) {
+                TapeRec r{T_CONCAT, GemmArgs(), h, sk.p, cat};
+                r.M = rows; r.C = hc; r.C2 = sk.C;
+                tape.push_back(r);
+            }
             const Res& r = up_res[i][j];
             ETAI_CHECK(r.cin == hc + sk.C, ETAI_ERR_STATE, "skip bookkeeping mismatch");
             h = resnet(cat, B, H, W, r, ctrl, i == 1 && j == 1, s);
@@ -611,12 +445,18 @@ void etai_unet::run_body(int io_dtype, int B, const etai_attn_ctrl* ctrl, cudaSt
                 upsample2x(h, up, B, H, W, hc, dt, s);
                 prof_end(ETAI_PROF_OTHER, e, 1, s);
             }
+            if (tape_on) {
+                TapeRec r{T_UPSAMPLE, GemmArgs(), h, nullptr, up};
+                r.B = B; r.H = H; r.W = W; r.C = hc;
+                tape.push_back(r);
+            }
             H *= 2; W *= 2;
             h = conv3x3(up, B, H, W, up_samp[i], 1, nullptr, nullptr, s);
         }
     }
     void* a = gnorm(h, B, (long)H * W, norm_out, 1e-5f, true, s);
     void* o = conv3x3(a, B, H, W, conv_out, 1, nullptr, nullptr, s);
+    last_out = o;
     if (!planning) {
         cudaEvent_t e = prof_begin(s);
         nhwc_to_nchw(o, dt, eps_out, io_dtype, B, 4, conv_out.cout, (long)H * W, s);
@@ -648,7 +488,8 @@ static std::string graph_key(int io_dtype, int B, const etai_attn_ctrl* c) {
 }
 
 void etai_unet::forward(const void* latent, float t, int io_dtype, int B, const etai_attn_ctrl* ctrl, void* eps_out,
-                        cudaStream_t user) {
+                        cudaStream_t user, bool train) {
+    bwd_batch = 0;  // any forward overwrites the activations a pending backward pass would read
     ETAI_CHECK(B >= 1 && B <= cfg.max_batch, ETAI_ERR_ARG, "forward: batch out of range");
     ETAI_CHECK(ctx_rows == B, ETAI_ERR_STATE, "forward: etai_unet_set_context must be called with the same batch first");
     const int L = cfg.ctx_len;
@@ -681,7 +522,22 @@ void etai_unet::forward(const void* latent, float t, int io_dtype, int B, const 
     }
     // ---- the schedule: eager the first time a key is seen, captured the second time, replayed afterwards ----
     bool done = false;
-    if (use_graphs && !prof_on) {
+    if (train) {  // eager, recorded on the tape, GEGLU un-fused: the activations stay in the arena for backward_ctx
+        ETAI_CHECK(bwd_enabled && B <= bwd_max_batch && !ctrl, ETAI_ERR_STATE,
+                   "forward_train: call etai_unet_enable_backward first (batch <= its max_batch, no attention control)");
+        tape.clear();
+        tape_on = true;
+        try {
+            run_body(io_dtype, B, nullptr, gs);
+        } catch (...) {
+            tape_on = false;
+            throw;
+        }
+        tape_on = false;
+        bwd_batch = B;
+        done = true;
+    }
+    if (!done && use_graphs && !prof_on) {
         GraphEntry& ge = graphs[graph_key(io_dtype, B, ctrl)];
         if (ge.exec) {
             CUDA_CHECK(cudaGraphLaunch(ge.exec, gs));
@@ -782,6 +638,252 @@ void etai_unet::plan_workspace() {
     workspace_bytes += (size_t)ctx_m * (kv_total + cfg.cross_dim) * esz + gws + tc_ws_bytes;
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// backward w.r.t. the text context (null-text inversion: modules/inversion/null_text_inversion.py:62-80)
+// -------------------------------------------------------------------------------------------------
+void* etai_unet::make_wT(const void* w, int n, int k, bool conv) {
+    auto it = wT.find(w);
+    if (it != wT.end()) return it->second;
+    void* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, (conv ? (size_t)n * 9 * k : (size_t)n * k) * esz));
+    bwd_owned.push_back(p);
+    if (conv) conv_weight_flip(w, p, n, k, dt, gs);
+    else transpose_2d(w, p, n, k, dt, gs);
+    launches += 1;
+    wT[w] = p;
+    return p;
+}
+
+// Reverse walk over the tape of the last train-mode forward.  grad[] maps an activation to the buffer holding dL/d(it);
+// only activations that depend on the context (everything downstream of the first cross-attention) get one.  The seed
+// (dL/d(conv_out result)) is taken from `seed`; the result is left in dkv (per-layer dK | dV columns).
+void etai_unet::backward_walk(int B, cudaStream_t s) {
+    const bool plan = garena.base == nullptr;
+    const int L = cfg.ctx_len;
+    std::unordered_set<const void*> dep;
+    for (const TapeRec& r : tape) {
+        bool d = r.kind == T_CROSS_ATTN || dep.count(r.x) || (r.x2 && dep.count(r.x2)) ||
+                 (r.kind == T_GEMM && r.g.residual && dep.count(r.g.residual));
+        if (d) dep.insert(r.y);
+    }
+    std::unordered_map<const void*, void*> grad;
+    auto add_grad = [&](const void* t, void* g, long n) {
+        auto it = grad.find(t);
+        if (it == grad.end()) { grad[t] = g; return; }
+        if (!plan) { add_inplace(it->second, g, n, dt, s); launches += 1; }
+    };
+    ETAI_CHECK(last_out && dep.count(last_out), ETAI_ERR_STATE, "backward: the recorded forward does not reach the context");
+    grad[last_out] = bwd_seed;
+    for (size_t ii = tape.size(); ii-- > 0;) {
+        const TapeRec& r = tape[ii];
+        if (!dep.count(r.y)) continue;
+        auto gi = grad.find(r.y);
+        if (gi == grad.end()) continue;
+        void* dy = gi->second;
+        switch (r.kind) {
+        case T_GEMM: {
+            const GemmArgs& g = r.g;
+            ETAI_CHECK(!g.geglu && g.ldc == g.N, ETAI_ERR_STATE, "backward: unexpected GEMM layout on the tape");
+            if (g.residual && dep.count(g.residual)) add_grad(g.residual, dy, g.M * g.N);
+            if (!dep.count(g.A)) break;
+            if (!g.conv) {
+                ETAI_CHECK(g.lda == g.K, ETAI_ERR_STATE, "backward: strided GEMM input on the tape");
+                void* dx = garena.alloc((size_t)g.M * g.K * esz);
+                if (!plan) {
+                    GemmArgs b;  // dx[M,K] = dy[M,N] * W[N,K]
+                    b.A = dy; b.W = make_wT(g.W, g.N, g.K, false); b.C = dx;
+                    b.M = g.M; b.N = g.K; b.K = g.N; b.lda = g.N; b.ldc = g.K; b.ldr = g.K;
+                    gemm(b, s);
+                }
+                add_grad(g.A, dx, g.M * g.K);
+            } else {
+                const int Cout = g.N, Cin = g.Cin, H = g.H, W = g.Wd;
+                const void* img = dy;
+                if (g.stride == 2) {  // adjoint of the stride-2 conv: zero-stuff dy to the input resolution, then a stride-1 conv
+                    void* z = garena.alloc((size_t)g.B * H * W * Cout * esz);
+                    if (!plan) { zero_stuff2x(dy, z, g.B, g.Ho, g.Wo, Cout, dt, s); launches += 1; }
+                    img = z;
+                }
+                const long Mi = (long)g.B * H * W;
+                void* dx = garena.alloc((size_t)Mi * Cin * esz);
+                if (!plan) {
+                    GemmArgs b;  // dx = conv3x3(dy, filter mirrored and transposed)
+                    b.A = img; b.W = make_wT(g.W, Cout, Cin, true); b.C = dx;
+                    b.M = Mi; b.N = Cin; b.K = 9 * Cout; b.ldc = Cin; b.ldr = Cin;
+                    b.conv = 1; b.B = g.B; b.H = H; b.Wd = W; b.Cin = Cout; b.stride = 1; b.Ho = H; b.Wo = W; b.pad = 1;
+                    gemm(b, s);
+                }
+                add_grad(g.A, dx, Mi * Cin);
+            }
+            break;
+        }
+        case T_GN: {
+            const long n = (long)r.B * r.HW * r.n.c;
+            void* dx = garena.alloc((size_t)n * esz);
+            if (!plan) { groupnorm_bwd(r.x, dy, r.n.g, r.n.b, dx, r.B, r.HW, r.n.c, 32, r.eps, r.silu, dt, s); launches += 1; }
+            add_grad(r.x, dx, n);
+            break;
+        }
+        case T_LN: {
+            const long n = r.M * r.n.c;
+            void* dx = garena.alloc((size_t)n * esz);
+            if (!plan) { layernorm_bwd(r.x, dy, r.n.g, dx, r.M, r.n.c, r.eps, dt, s); launches += 1; }
+            add_grad(r.x, dx, n);
+            break;
+        }
+        case T_SELF_ATTN: {
+            const int C = r.C;
+            const long M = (long)r.B * r.HW;
+            char* dqkv = (char*)garena.alloc((size_t)M * 3 * C * esz);
+            if (!plan) {
+                SelfAttnBwdArgs a;
+                const char* qkv = (const char*)r.x;
+                a.q = qkv; a.k = qkv + (size_t)C * esz; a.v = qkv + (size_t)2 * C * esz; a.o = r.y; a.dout = dy;
+                a.dq = dqkv; a.dk = dqkv + (size_t)C * esz; a.dv = dqkv + (size_t)2 * C * esz;
+                a.lse = lse_buf; a.dsum = lse_buf + (size_t)bwd_max_batch * r.heads * cfg.latent_hw * cfg.latent_hw;
+                a.B = r.B; a.N = (int)r.HW; a.heads = r.heads; a.d = r.d;
+                a.ldq = a.ldk = a.ldv = 3 * C; a.ldo = C; a.lddo = C; a.lddq = a.lddk = a.lddv = 3 * C;
+                a.scale = r.scale; a.dtype = dt;
+                attention_bwd(a, s);
+                launches += 2;
+            }
+            add_grad(r.x, dqkv, M * 3 * C);
+            break;
+        }
+        case T_CROSS_ATTN: {
+            const int C = r.C;
+            const long M = (long)r.B * r.HW;
+            const bool want_dq = dep.count(r.x) != 0;
+            void* dq = want_dq ? garena.alloc((size_t)M * C * esz) : nullptr;
+            size_t pb = cross_attention_bwd_partial_bytes(r.B, (int)r.HW, L, C, r.d);
+            if (pb > cross_part_need) cross_part_need = pb;
+            if (!plan) {
+                CrossAttnBwdArgs a;
+                a.q = r.x; a.kv = kv_cache; a.dout = dy; a.dq = dq; a.part = cross_part; a.dkv = dkv;
+                a.B = r.B; a.N = (int)r.HW; a.L = L; a.heads = r.heads; a.d = r.d;
+                a.ldq = C; a.ldkv = kv_total; a.lddo = C; a.lddq = C; a.ld_dkv = kv_total;
+                a.koff = r.kv_off; a.voff = r.kv_off + C; a.kv_off = r.kv_off; a.scale = r.scale; a.dtype = dt;
+                cross_attention_bwd(a, s);
+                launches += 2;
+            }
+            if (want_dq) add_grad(r.x, dq, M * C);
+            break;
+        }
+        case T_GEGLU: {
+            const long n = r.M * 2 * r.C;
+            void* du = garena.alloc((size_t)n * esz);
+            if (!plan) { geglu_bwd(r.x, dy, du, r.M, r.C, dt, s); launches += 1; }
+            add_grad(r.x, du, n);
+            break;
+        }
+        case T_CONCAT: {
+            const void* in[2] = {r.x, r.x2};
+            const int cw[2] = {r.C, r.C2}, off[2] = {0, r.C};
+            for (int k = 0; k < 2; ++k) {
+                if (!dep.count(in[k])) continue;
+                auto it = grad.find(in[k]);
+                const bool acc = it != grad.end();
+                void* dst = acc ? it->second : garena.alloc((size_t)r.M * cw[k] * esz);
+                if (!plan) { slice_cols(dy, r.C + r.C2, off[k], cw[k], dst, acc, r.M, dt, s); launches += 1; }
+                if (!acc) grad[in[k]] = dst;
+            }
+            break;
+        }
+        case T_UPSAMPLE: {
+            const long n = (long)r.B * r.H * r.W * r.C;
+            void* din = garena.alloc((size_t)n * esz);
+            if (!plan) { upsample2x_bwd(dy, din, r.B, r.H, r.W, r.C, dt, s); launches += 1; }
+            add_grad(r.x, din, n);
+            break;
+        }
+        }
+    }
+    // d(ctx) = d(K|V of all layers)[B*L, kv_total] * W_kv[kv_total, cross_dim]
+    const long Mc = (long)B * L;
+    void* dkv_t = dkv;
+    if (dt != ETAI_F32) {
+        dkv_t = garena.alloc((size_t)Mc * kv_total * esz);
+        if (!plan) { convert(dkv, ETAI_F32, dkv_t, dt, Mc * kv_total, s); launches += 1; }
+    }
+    bwd_dctx = garena.alloc((size_t)Mc * cfg.cross_dim * esz);
+    if (!plan) {
+        GemmArgs b;
+        b.A = dkv_t; b.W = make_wT(kv_all.w, kv_all.n, kv_all.k, false); b.C = bwd_dctx;
+        b.M = Mc; b.N = cfg.cross_dim; b.K = kv_total; b.lda = kv_total; b.ldc = cfg.cross_dim; b.ldr = cfg.cross_dim;
+        gemm(b, s);
+    }
+}
+
+void etai_unet::enable_backward(int max_batch) {
+    if (bwd_enabled && max_batch <= bwd_max_batch) return;
+    ETAI_CHECK(!bwd_enabled, ETAI_ERR_STATE, "enable_backward: already enabled with a smaller max_batch");
+    ETAI_CHECK(max_batch >= 1 && max_batch <= cfg.max_batch, ETAI_ERR_ARG, "enable_backward: max_batch out of range");
+    CUDA_CHECK(cudaStreamSynchronize(gs));
+    bwd_max_batch = max_batch;
+    // dry run: a train-mode forward + its backward walk with null arenas give the gradient arena size
+    char* base = arena.base;
+    const size_t peak = arena.peak;
+    arena.base = nullptr;
+    arena.peak = 0;
+    tape.clear();
+    tape_on = true;
+    run_body(ETAI_F32, max_batch, nullptr, 0);
+    tape_on = false;
+    const size_t train_peak = arena.peak;
+    arena.base = base;
+    arena.peak = peak > train_peak ? peak : train_peak;
+    ETAI_CHECK(train_peak + 4096 <= arena.cap, ETAI_ERR_NOMEM,
+               "enable_backward: the activation arena is too small for a train-mode forward of this batch (create the engine "
+               "with a larger max_batch)");
+    garena.base = nullptr; garena.cap = 0; garena.peak = 0; garena.reset();
+    const long hw = (long)cfg.latent_hw * cfg.latent_hw;
+    garena.alloc((size_t)max_batch * 4 * hw * sizeof(float));              // scaled copy of d_eps
+    bwd_seed = garena.alloc((size_t)max_batch * hw * conv_out.cout * esz);
+    cross_part_need = 0;
+    backward_walk(max_batch, 0);
+    tape.clear();
+    size_t need = garena.peak + 4096;
+    void* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, need));
+    garena.base = (char*)p; garena.cap = need; garena.reset();
+    CUDA_CHECK(cudaMalloc((void**)&dkv, (size_t)max_batch * cfg.ctx_len * kv_total * sizeof(float)));
+    CUDA_CHECK(cudaMalloc((void**)&cross_part, cross_part_need ? cross_part_need : 256));
+    CUDA_CHECK(cudaMalloc((void**)&lse_buf, (size_t)2 * max_batch * cfg.heads * hw * sizeof(float)));
+    CUDA_CHECK(cudaMalloc((void**)&scale_dev, 256));
+    workspace_bytes += need + (size_t)max_batch * cfg.ctx_len * kv_total * 4 + cross_part_need + 2 * max_batch * cfg.heads * hw * 4;
+    bwd_enabled = true;
+}
+
+void etai_unet::backward_ctx(const float* d_eps, int B, float* d_ctx, cudaStream_t user) {
+    ETAI_CHECK(bwd_enabled && bwd_batch == B && B >= 1, ETAI_ERR_STATE,
+               "backward_ctx: needs the train-mode forward of the same batch immediately before");
+    const long hw = (long)cfg.latent_hw * cfg.latent_hw, ne = (long)B * 4 * hw;
+    CUDA_CHECK(cudaEventRecord(ev_in, user));
+    CUDA_CHECK(cudaStreamWaitEvent(gs, ev_in, 0));
+    cudaStream_t s = gs;
+    garena.reset();
+    const bool scaled = dt != ETAI_F32;  // 16-bit gradients: normalise the seed to max|.| = 16, undo at the end (the pass is linear)
+    float* de = (float*)garena.alloc((size_t)bwd_max_batch * 4 * hw * sizeof(float));
+    bwd_seed = garena.alloc((size_t)bwd_max_batch * hw * conv_out.cout * esz);
+    const float* src = d_eps;
+    if (scaled) {
+        absmax_scale(d_eps, ne, 16.0f, scale_dev, s);
+        scale_by_device_scalar(d_eps, de, scale_dev, false, ne, ETAI_F32, s);
+        launches += 2;
+        src = de;
+    }
+    nchw_to_nhwc(src, ETAI_F32, bwd_seed, dt, B, 4, conv_out.cout, hw, s);
+    launches += 1;
+    backward_walk(B, s);
+    const long nc = (long)B * cfg.ctx_len * cfg.cross_dim;
+    convert(bwd_dctx, dt, d_ctx, ETAI_F32, nc, s);
+    launches += 1;
+    if (scaled) { scale_by_device_scalar(d_ctx, d_ctx, scale_dev, true, nc, ETAI_F32, s); launches += 1; }
+    CUDA_CHECK(cudaEventRecord(ev_out, gs));
+    CUDA_CHECK(cudaStreamWaitEvent(user, ev_out, 0));
+}
+
 // -------------------------------------------------------------------------------------------------
 // C ABI
 // -------------------------------------------------------------------------------------------------
@@ -867,6 +969,10 @@ int etai_unet_destroy(etai_unet* h) {
     if (h->map16_buf) cudaFree(h->map16_buf);
     if (h->store_part_buf) cudaFree(h->store_part_buf);
     if (h->stage) cudaFree(h->stage);
+    for (void* p : h->bwd_owned) cudaFree(p);
+    void* bw[] = {h->garena.base, h->dkv, h->cross_part, h->lse_buf, h->scale_dev};
+    for (void* p : bw)
+        if (p) cudaFree(p);
     delete h;
     return ETAI_OK;
 }
@@ -955,6 +1061,31 @@ int etai_unet_forward(etai_unet* h, const void* latent, float t, int32_t io_dtyp
                        ETAI_ERR_ARG, "ctrl: store rows");
     }
     h->forward(latent, t, io_dtype, B, ctrl, eps_out, (cudaStream_t)stream);
+    ETAI_API_END
+}
+
+/* ---- null-text inversion support ---- */
+int etai_unet_enable_backward(etai_unet* h, int32_t max_batch) {
+    ETAI_API_BEGIN
+    ETAI_CHECK(h, ETAI_ERR_ARG, "enable_backward: null handle");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    h->enable_backward(max_batch);
+    ETAI_API_END
+}
+
+int etai_unet_forward_train(etai_unet* h, const void* latent, float t, int32_t io_dtype, int32_t B, void* eps_out, void* stream) {
+    ETAI_API_BEGIN
+    ETAI_CHECK(h && latent && eps_out, ETAI_ERR_ARG, "forward_train: null argument");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    h->forward(latent, t, io_dtype, B, nullptr, eps_out, (cudaStream_t)stream, /*train=*/true);
+    ETAI_API_END
+}
+
+int etai_unet_backward_ctx(etai_unet* h, const float* d_eps, int32_t B, float* d_ctx_out, void* stream) {
+    ETAI_API_BEGIN
+    ETAI_CHECK(h && d_eps && d_ctx_out, ETAI_ERR_ARG, "backward_ctx: null argument");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    h->backward_ctx(d_eps, B, d_ctx_out, (cudaStream_t)stream);
     ETAI_API_END
 }
 

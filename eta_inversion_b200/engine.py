@@ -241,6 +241,34 @@ class UNetEngine:
 
     __call__ = forward
 
+    # ---- gradient w.r.t. the text context (null-text inversion) -------------------------------------------------------
+    def enable_backward(self, max_batch: int = 1) -> None:
+        with torch.cuda.device(self.device):
+            check(self._lib.etai_unet_enable_backward(self._h, int(max_batch)))
+
+    def forward_train(self, sample: torch.Tensor, timestep, encoder_hidden_states: torch.Tensor) -> torch.Tensor:
+        """``unet(sample, t, ctx)["sample"]`` keeping the activations for :meth:`backward_ctx` (no attention control)."""
+        _require_cuda(sample, "sample")
+        ctx = encoder_hidden_states.detach()
+        ctx = ctx if ctx.is_contiguous() else ctx.contiguous()
+        self.set_context(ctx)  # the context changes every optimisation step: always re-project K/V
+        self._ctx_key = None
+        out = torch.empty_like(sample)
+        t = float(timestep.item() if torch.is_tensor(timestep) else timestep)
+        with torch.cuda.device(self.device):
+            check(self._lib.etai_unet_forward_train(self._h, ptr(sample), t, dtype_code(sample.dtype), sample.shape[0], ptr(out),
+                                                    stream_ptr()))
+        return out
+
+    def backward_ctx(self, d_eps: torch.Tensor) -> torch.Tensor:
+        """d(ctx) [B,77,768] fp32 for the train-mode forward made just before; ``d_eps``: dL/d(eps), [B,4,hw,hw]."""
+        d = d_eps.detach().float().contiguous()
+        _require_cuda(d, "d_eps")
+        out = torch.empty((d.shape[0], self.ctx_len, self.cross_dim), dtype=torch.float32, device=d.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.etai_unet_backward_ctx(self._h, ptr(d), d.shape[0], ptr(out), stream_ptr()))
+        return out
+
 
 # ------------------------------------------------------------------------------------------------
 # single ops (unit parity + roofline runs)

@@ -136,7 +136,7 @@ class DiffusionInversion:
     def _embed_uncached(self, text: str) -> torch.Tensor:
         tok = self.model.tokenizer([text], padding="max_length", max_length=self.model.tokenizer.model_max_length,
                                    truncation=True, return_tensors="pt")
-        return self.model.text_encoder(h2d(tok.input_ids, self.model.device))[0].float()
+        return self.model.text_encoder(tok.input_ids)[0].float()  # ids are host data; the native tower uploads them
 
     def create_context(self, prompt: str, negative_prompt: str = "") -> torch.Tensor:
         text_embeddings = self._embed(prompt)

@@ -195,6 +195,10 @@ class EtaInversion(DiffusionInversion):
         if eta > 0 and cand.shape[0] > 1:
             losses, best = E.eta_noise_losses(eps_raw, latent, src_prev, a_t, a_p, g, eta, var, cand)
             self.picks.append(best)  # device int32 [1] per step, never read inside the loop (tests / diagnostics)
+        else:
+            # eta == 0 (or one candidate): every candidate reproduces the same latent, the reference's argmin over equal
+            # losses returns 0 (eta_inversion.py:363)
+            self.picks.append(torch.zeros(1, dtype=torch.int32))
         eta_map = None
         delta_mask = None
         if self.mask_mode_cfg is not None:

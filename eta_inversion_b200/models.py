@@ -18,7 +18,7 @@ import torch
 from . import synthetic
 from .engine import UNetEngine
 from .inverse_schedulers import DDIMScheduler
-from .vae import AutoencoderKL, make_text_encoder
+from .vae import CLIPTextEngine, VAEEngine
 
 
 class StablePreprocess:
@@ -152,18 +152,17 @@ def load_diffusion_model(model: str = "synthetic-sd15", device: str = "cuda", pr
         raise RuntimeError("etai: the engine runs on CUDA devices only (no CPU fallback)")
     dev = torch.device(device if ":" in str(device) else f"cuda:{torch.cuda.current_device()}")
     print(f"Loading model {model} ({variant}) ...")
-    if variant == "fp32":
-        # parity mode: the torch-side VAE / text encoder must not silently drop to TF32
-        torch.backends.cudnn.allow_tf32 = False
-        torch.backends.cuda.matmul.allow_tf32 = False
     usd = unet_state_dict if unet_state_dict is not None else synthetic.random_state_dict(synthetic.unet_param_spec(), seed)
     unet = UNetEngine(usd, dtype=dtype, device=dev, max_batch=max_batch)
     del usd
-    vae = AutoencoderKL().eval().requires_grad_(False)
-    vae.load_state_dict(vae_state_dict if vae_state_dict is not None
-                        else synthetic.random_state_dict(synthetic.vae_param_spec(), seed + 1), strict=True)
-    vae = vae.to(dev, dtype).to(memory_format=torch.channels_last)
-    # 16-bit variants run CLIP in 16-bit as the reference does
-    text_encoder = (text_encoder if text_encoder is not None else make_text_encoder(seed)).to(dev, dtype)
+    # VAE and CLIP text tower: native handles too (csrc/vae.cu, csrc/clip.cu); 16-bit variants run both in 16-bit as the
+    # reference does.  The handles serialise their own calls, so lanes / pipelined groups share them.
+    vae = VAEEngine(vae_state_dict if vae_state_dict is not None
+                    else synthetic.random_state_dict(synthetic.vae_param_spec(), seed + 1), dtype=dtype, device=dev, max_batch=2)
+    if isinstance(text_encoder, CLIPTextEngine):
+        pass
+    else:  # a transformers CLIPTextModel (real checkpoint) or the seeded random-init tower: weights + config only
+        text_encoder = CLIPTextEngine.from_transformers(
+            text_encoder if text_encoder is not None else synthetic.make_text_encoder(seed), dtype=dtype, device=dev)
     pipe = EtaiPipeline(unet, vae, text_encoder, tokenizer if tokenizer is not None else SyntheticTokenizer(), sd_scheduler(), dev)
     return pipe, (StablePreprocess(str(dev), size=512, **(preproc_args or {})), StablePostProc())

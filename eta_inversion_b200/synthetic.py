@@ -31,6 +31,8 @@ TOKEN_EMB_GAIN = 32.0
 # variance, a variance-preserving random encoder gives std ~0.13 after it; then conv_in's bias and the time embedding swamp
 # the image content and every UNet feature map is spatially constant.
 VAE_LATENT_GAIN = 16.0
+# Per-pixel white noise of the synthetic image (random convolutions amplify it into spatially incoherent features).
+IMAGE_NOISE = 0.05
 
 
 def _resnet(prefix: str, cin: int, cout: int, temb: int | None) -> Spec:
@@ -184,7 +186,7 @@ def synthetic_image(seed: int = 0, size: int = 512) -> torch.Tensor:
             fx, fy, ph = (torch.rand(3, generator=g) * torch.tensor([6.0, 6.0, 6.2832])).tolist()
             amp = float(torch.rand(1, generator=g)) * 0.5
             img[c] += amp * torch.sin(6.2832 * (fx * xx + fy * yy) + ph)
-    img += 0.05 * torch.randn(3, size, size, generator=g)
+    img += IMAGE_NOISE * torch.randn(3, size, size, generator=g)
     img = 0.5 * img / img.abs().max()
     for _ in range(3):
         cx, cy, rx, ry = (torch.rand(4, generator=g) * torch.tensor([0.6, 0.6, 0.15, 0.15]) + torch.tensor([0.2, 0.2, 0.1, 0.1])).tolist()

@@ -152,6 +152,23 @@ ETAI_EXPORT int etai_unet_set_context(etai_unet* h, const void* ctx, int32_t io_
 ETAI_EXPORT int etai_unet_forward(etai_unet* h, const void* latent, float t, int32_t io_dtype, int32_t B,
                       const etai_attn_ctrl* ctrl, void* eps_out, void* stream);
 
+/* ---- null-text inversion: gradient of the UNet output w.r.t. the text context ------------------------------------
+ * replaces `loss.backward()` through `unet(latent_cur, t, uncond_embeddings)` at
+ * modules/inversion/null_text_inversion.py:75-80 (the only differentiated input is the [1,77,768] uncond embedding).
+ *   etai_unet_enable_backward  once per handle: sizes the gradient arena for `max_batch` rows (1 for NTI); the dgrad copies of
+ *                              the weights (W^T, mirrored conv filters) are made on first use (+1x weight memory).
+ *   etai_unet_forward_train    like etai_unet_forward (same context protocol, no attention control) but eager, with GEGLU
+ *                              un-fused and every activation kept in the arena for the backward pass.
+ *   etai_unet_backward_ctx     d_ctx[B,77,768] = (d eps / d ctx)^T d_eps for the train-mode forward made immediately before
+ *                              on this handle (any other forward in between invalidates it).  d_eps: fp32 [B,4,hw,hw] NCHW;
+ *                              d_ctx_out: fp32.  Data gradients only (conv dgrad = conv3x3 with the mirrored filter on the same
+ *                              tcgen05 kernel, linear dgrad = GEMM with W^T, flash-style attention backward, norm backward);
+ *                              16-bit engines scale the seed to max|.| = 16 on the device and undo it at the end. */
+ETAI_EXPORT int etai_unet_enable_backward(etai_unet* h, int32_t max_batch);
+ETAI_EXPORT int etai_unet_forward_train(etai_unet* h, const void* latent, float t, int32_t io_dtype, int32_t B, void* eps_out,
+                            void* stream);
+ETAI_EXPORT int etai_unet_backward_ctx(etai_unet* h, const float* d_eps, int32_t B, float* d_ctx_out, void* stream);
+
 /* Instrumentation.  etai_unet_launch_count: kernels launched by this handle since create (the bench's
  * `gpu_launches` claim).  etai_unet_profile: reads (and clears) the per-category device time accumulated since the
  * previous call -- CUDA events recorded around every op on the caller's stream -- then switches recording on/off.
@@ -163,6 +180,51 @@ ETAI_EXPORT int etai_unet_profile(etai_unet* h, int32_t enable, float* ms_out, i
 
 /* Bytes of device memory held by the handle (weights + workspace). */
 ETAI_EXPORT int64_t etai_unet_device_bytes(const etai_unet* h);
+
+/* ---- VAE ----------------------------------------------------------------------------------------
+ * replaces `model.vae` of the reference pipeline object: `vae.encode(image)['latent_dist'].mean` and
+ * `vae.decode(latent)['sample']` (modules/inversion/diffusion_inversion.py:183-208; the 0.18215 latent scaling stays with
+ * the caller like in the reference).  Weights: `vae.state_dict()` of diffusers' AutoencoderKL (SD-1.x layout).
+ * A handle serialises its own calls, so several threads / streams may share it. */
+typedef struct etai_vae etai_vae; /* opaque */
+typedef struct {
+    int32_t dtype;                 /* storage dtype of weights + activations */
+    int32_t math_mode;             /* ETAI_MATH_* */
+    int32_t block_out_channels[4]; /* SD-1.x: 128,256,512,512 */
+    int32_t image_hw;              /* 512 */
+    int32_t max_batch;             /* images per call */
+} etai_vae_cfg;
+ETAI_EXPORT int etai_vae_create(etai_vae** out, const etai_vae_cfg* cfg, const etai_tensor* weights, int32_t n_weights,
+                    int32_t device);
+ETAI_EXPORT int etai_vae_destroy(etai_vae* h);
+/* image: [B,3,hw,hw] NCHW in [-1,1]; mean_out: [B,4,hw/8,hw/8] NCHW (the posterior mean), both of io_dtype */
+ETAI_EXPORT int etai_vae_encode(etai_vae* h, const void* image, int32_t io_dtype, int32_t B, void* mean_out, void* stream);
+/* latent: [B,4,hw/8,hw/8] (already divided by 0.18215); image_out: [B,3,hw,hw], both of io_dtype */
+ETAI_EXPORT int etai_vae_decode(etai_vae* h, const void* latent, int32_t io_dtype, int32_t B, void* image_out, void* stream);
+ETAI_EXPORT int64_t etai_vae_launch_count(const etai_vae* h);
+ETAI_EXPORT int64_t etai_vae_device_bytes(const etai_vae* h);
+
+/* ---- CLIP text tower ---------------------------------------------------------------------------
+ * replaces `model.text_encoder(input_ids)[0]` (modules/inversion/diffusion_inversion.py:210-247).  Weights:
+ * `text_encoder.state_dict()` of transformers' CLIPTextModel (keys "text_model.*").  Causal mask only (the reference
+ * passes no attention mask).  Any number of prompts <= max_batch per call. */
+typedef struct etai_clip etai_clip; /* opaque */
+typedef struct {
+    int32_t dtype, math_mode;
+    int32_t vocab;     /* 49408 */
+    int32_t hidden;    /* 768 */
+    int32_t layers;    /* 12 */
+    int32_t heads;     /* 12 (head dim must be 64) */
+    int32_t ffn;       /* 3072, quick-GELU */
+    int32_t max_len;   /* 77 */
+    int32_t max_batch; /* prompts per call */
+} etai_clip_cfg;
+ETAI_EXPORT int etai_clip_create(etai_clip** out, const etai_clip_cfg* cfg, const etai_tensor* weights, int32_t n_weights,
+                     int32_t device);
+ETAI_EXPORT int etai_clip_destroy(etai_clip* h);
+/* input_ids: HOST int32 [B,max_len]; out: device [B,max_len,hidden] of io_dtype = last_hidden_state (final LayerNorm applied) */
+ETAI_EXPORT int etai_clip_encode(etai_clip* h, const int32_t* input_ids, int32_t B, void* out, int32_t io_dtype, void* stream);
+ETAI_EXPORT int64_t etai_clip_launch_count(const etai_clip* h);
 
 /* ---- scheduler --------------------------------------------------------------------------------
  * One fused kernel for: CFG combine (diffusion_inversion.py:283-284, eta_inversion.py:328)

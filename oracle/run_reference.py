@@ -193,6 +193,12 @@ def run_scenario(name, pipe, syn):
     ref_ptp.LocalBlend.get_mask = orig_lb
     inv_lat = [as_tensor(l).detach().numpy() for l in inv_box["res"]["latents"]]
     inv_eps = [e.detach().numpy() for e in inv_box["res"]["noise_preds"] if e is not None]
+    # null-text inversion also calls predict_step_backward inside its optimisation (one source row); those steps are kept
+    # apart from the edit loop's (source + target rows)
+    nti_lat = [x for x in rec["bwd_latents"] if x.shape != rec["bwd_latents"][-1].shape]
+    nti_eps = [x for x in rec["bwd_eps"] if x.shape != rec["bwd_eps"][-1].shape]
+    rec["bwd_latents"] = [x for x in rec["bwd_latents"] if x.shape == rec["bwd_latents"][-1].shape]
+    rec["bwd_eps"] = [x for x in rec["bwd_eps"] if x.shape == rec["bwd_eps"][-1].shape]
     ki, kb = keep_steps(len(inv_lat)), keep_steps(len(rec["bwd_latents"]))
     out = dict(
         inv_latents=np.stack([inv_lat[i] for i in ki]), inv_steps_kept=np.array(ki),
@@ -204,6 +210,8 @@ def run_scenario(name, pipe, syn):
         image_mean=np.array([res["image"].mean().item(), res["image_inv"].mean().item()]),
         seconds=np.array(dt),
     )
+    if nti_lat:
+        out["nti_latents"], out["nti_eps"] = np.stack(nti_lat), np.stack(nti_eps)
     if lb_frac:
         out["localblend_mask_fraction"] = np.array(lb_frac)
     if name in FULL_IMAGE:  # PSNR gate of the 16-bit engine against the reference's fp32 image

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--editor", default="ptp")
     ap.add_argument("--long", action="store_true")
     ap.add_argument("--vae-gain", type=float, default=1.0, dest="vae_gain")
+    ap.add_argument("--image-noise", type=float, default=0.05, dest="image_noise")
     args = ap.parse_args()
     rr._setup_paths()
     torch.set_num_threads(os.cpu_count())
@@ -35,6 +36,7 @@ def main():
         syn.ATTN2_QK_GAIN = gain
         syn.TOKEN_EMB_GAIN = args.tok_gain
         syn.VAE_LATENT_GAIN = args.vae_gain
+        syn.IMAGE_NOISE = args.image_noise
         pipe = sd15.build_pipeline(syn.random_state_dict(syn.unet_param_spec(), 0),
                                    syn.random_state_dict(syn.vae_param_spec(), 1), seed=0)
         inverter = modules.load_inverter(model=pipe, type="etainv", scheduler="ddim", num_inference_steps=args.steps,

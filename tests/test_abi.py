@@ -64,5 +64,5 @@ def test_registry_surface_matches_reference():
     assert set(etai.get_edit_methods()) == {"simple", "ptp", "masactrl", "pnp", "pix2pix_zero", "invedit"}
     with pytest.raises(NotImplementedError):
         etai.load_editor(type="pix2pix_zero", inverter=None)
-    with pytest.raises(NotImplementedError):
-        etai.load_inverter(type="nti", model=None)
+    from eta_inversion_b200.inversion.null_text_inversion import NullTextInversion
+    assert etai._inverters["nti"] is NullTextInversion

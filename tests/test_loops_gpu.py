@@ -26,7 +26,7 @@ def _t(x):
     return torch.cat([_t(v) for v in x]) if isinstance(x, (list, tuple)) else x
 
 
-NOT_BUILT = {"nti_ptp_replace_3": "null-text inversion needs the UNet dgrad path, which is not built"}  # scenario name -> reason (kept so the parametrised list always equals the golden list)
+NOT_BUILT = {}  # scenario name -> reason (kept so the parametrised list always equals the golden list)
 FULL_SIZE = ("diffinv_simple_10", "etainv_ptp_replace_50", "etainv_masactrl_50")  # BASELINE.json configs 1-3 at their step count
 
 
@@ -77,6 +77,13 @@ def test_fp32_trajectory_matches_reference(pipe_fp32, name):
     gold = np.load(GOLDEN / f"{name}.npz")
     res, rec, inverter = run_scenario(pipe_fp32, name)
     _FP32_IMAGES[name] = (res["image"].float().cpu(), res["image_inv"].float().cpu())
+    if "nti_latents" in gold.files:  # null-text inversion also steps (one source row) inside its optimisation loop
+        nti = torch.stack([l.cpu() for l in rec["bwd"] if l.shape != rec["bwd"][-1].shape])
+        rec["bwd"] = [l for l in rec["bwd"] if l.shape == rec["bwd"][-1].shape]
+        err_nti = (nti - torch.from_numpy(gold["nti_latents"])).abs().amax(dim=(1, 2, 3, 4))
+        print(f"{name}: latents after each optimised null-text step max-abs {err_nti.tolist()}; inner steps "
+              f"{inverter.inner_steps_taken}")
+        assert err_nti.max() < TOL_LATENT
     inv = torch.stack([_t(l).cpu() for l in rec["inv"]["latents"]])[torch.from_numpy(gold["inv_steps_kept"])]
     err_inv = (inv - torch.from_numpy(gold["inv_latents"])).abs().amax(dim=(1, 2, 3, 4))
     bwd = torch.stack([l.cpu() for l in rec["bwd"]])[torch.from_numpy(gold["bwd_steps_kept"])]

@@ -17,23 +17,7 @@ def test_pipelined_groups_match_sequential():
     from eta_inversion_b200.models import clone_pipeline
 
     pipe, _ = etai.load_diffusion_model("synthetic-sd15", "cuda:0", variant="fp32", max_batch=8)
-    # The torch-side VAE encoder and text encoder (cuDNN / cuBLAS) are not bit-reproducible across streams (workspace-
-    # dependent algorithm choices); memoise them by input content so that the comparison below isolates what this
-    # test is about: the engine, the lock-step merge and the stream plumbing.
-    import threading
-    lock, memo = threading.Lock(), {}
-
-    def memoised(fn, tag):
-        def call(x, *a, **k):
-            key = (tag, tuple(x.shape), float(x.double().sum()), float((x.double() ** 2).sum()))
-            with lock:
-                if key not in memo:
-                    memo[key] = fn(x, *a, **k)
-                    torch.cuda.current_stream().synchronize()
-                return memo[key]
-        return call
-    pipe.vae.encode = memoised(pipe.vae.encode, "vae")
-    pipe.text_encoder.forward = memoised(pipe.text_encoder.forward, "clip")
+    # VAE and text tower are native and bit-reproducible (fixed-order reductions), like the UNet: no memoisation needed
     pipe2 = clone_pipeline(pipe)
 
     def make_editor(p):

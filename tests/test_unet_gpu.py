@@ -43,3 +43,65 @@ def test_unet_fp16_close_to_golden(engine_fp16, t):
     rel = ((out - gold).norm() / gold.norm()).item()
     print(f"fp16 UNet t={t}: rel-L2 err {rel:.3e}, max-abs {(out - gold).abs().max():.3e}")
     assert rel < 2e-2
+
+
+# ---- gradient w.r.t. the text context (null-text inversion: modules/inversion/null_text_inversion.py:75-80) ---------
+def _oracle_grad(unet_weights, x, ctx, t, w):
+    """d sum(eps * w) / d ctx by torch autograd through the oracle UNet (CPU fp32)."""
+    from oracle import sd15
+    unet = sd15.UNet2DConditionModel().eval().requires_grad_(False)
+    unet.load_state_dict(unet_weights, strict=True)
+    c = ctx.clone().requires_grad_(True)
+    with torch.enable_grad():
+        eps = unet(x, torch.tensor(t), encoder_hidden_states=c)["sample"]
+        (eps * w).sum().backward()
+    return eps.detach(), c.grad.detach()
+
+
+@pytest.fixture(scope="module")
+def ctx_grad_case(unet_weights):
+    g = torch.Generator().manual_seed(4321)
+    x = torch.randn((1, 4, 64, 64), generator=g)
+    ctx = torch.randn((1, 77, 768), generator=g)
+    w = torch.randn((1, 4, 64, 64), generator=g) / (4 * 64 * 64)  # like d(mse)/d(eps): tiny per-element values
+    eps, grad = _oracle_grad(unet_weights, x, ctx, 501, w)
+    return x, ctx, w, eps, grad
+
+
+def test_unet_backward_ctx_fp32_matches_autograd(engine_fp32, ctx_grad_case):
+    x, ctx, w, eps_ref, grad_ref = ctx_grad_case
+    engine_fp32.enable_backward(1)
+    eps = engine_fp32.forward_train(x.cuda(), 501, ctx.cuda())
+    grad = engine_fp32.backward_ctx(w.cuda()).cpu()
+    err_f = (eps.cpu() - eps_ref).abs().max().item()
+    rel = ((grad - grad_ref).norm() / grad_ref.norm()).item()
+    print(f"train-mode forward max-abs {err_f:.2e}; d(ctx): rel-L2 {rel:.2e}, max-abs {(grad - grad_ref).abs().max():.2e} "
+          f"(|grad| max {grad_ref.abs().max():.2e})")
+    assert err_f < 5e-4
+    assert rel < 1e-3
+    # deterministic (no atomics): a second forward/backward pair reproduces the gradient bit for bit
+    engine_fp32.forward_train(x.cuda(), 501, ctx.cuda())
+    assert torch.equal(engine_fp32.backward_ctx(w.cuda()).cpu(), grad)
+    # the plain forward is unchanged by train mode
+    plain = engine_fp32(x.cuda(), 501, encoder_hidden_states=ctx.cuda())["sample"]
+    assert (plain - eps).abs().max().item() < 1e-5
+
+
+def test_unet_backward_ctx_fp16_close(engine_fp16, ctx_grad_case):
+    x, ctx, w, eps_ref, grad_ref = ctx_grad_case
+    engine_fp16.enable_backward(1)
+    engine_fp16.forward_train(x.cuda(), 501, ctx.cuda())
+    grad = engine_fp16.backward_ctx(w.cuda()).cpu()
+    rel = ((grad - grad_ref).norm() / grad_ref.norm()).item()
+    cos = torch.nn.functional.cosine_similarity(grad.flatten(), grad_ref.flatten(), dim=0).item()
+    print(f"fp16 d(ctx): rel-L2 {rel:.2e}, cosine {cos:.5f}")
+    assert torch.isfinite(grad).all()
+    assert rel < 5e-2 and cos > 0.998
+
+
+def test_backward_ctx_requires_train_forward(engine_fp32):
+    x, ctx = _inputs()
+    engine_fp32.enable_backward(1)
+    engine_fp32(x[:1].cuda().contiguous(), 501, encoder_hidden_states=ctx[:1].cuda().contiguous())
+    with pytest.raises(RuntimeError, match="train-mode forward"):
+        engine_fp32.backward_ctx(torch.zeros((1, 4, 64, 64), device="cuda"))
