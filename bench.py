@@ -34,6 +34,9 @@ PTP_CFG = dict(is_replace_controller=True, cross_replace_steps={"default_": .8},
                blend_words=[["cat"], ["tiger"]], equilizer_params={"words": ["tiger"], "values": [2]})
 INV_CFG = dict(edit_word_idx=(1, 1))
 ROWS_PER_EDIT = lambda steps: steps * 2 + steps * 4  # noqa: E731  (eta_inversion.py:319-328: B=2 inversion, B=4 edit)
+# rows the engine computes: at guidance_scale_fwd = 1 (the default) the inversion's unconditional row has weight exactly 0
+# in the reference's combine u + 1*(c - u) and is not computed (EtaInversion.skip_zero_weight_uncond)
+ROWS_COMPUTED = lambda steps, skip: steps * (1 if skip else 2) + steps * 4  # noqa: E731
 
 
 def peaks():
@@ -182,6 +185,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cobatch", type=int, default=4,
                     help="independent edits walked in lock step per step on each GPU (they share every UNet forward)")
+    ap.add_argument("--reference-rows", action="store_true", dest="reference_rows",
+                    help="also compute the inversion's zero-weight unconditional rows, like the reference (300 instead of 250 "
+                         "UNet rows per edit; same results)")
     ap.add_argument("--pipes", type=int, default=2,
                     help="lock-step groups in flight per GPU, each on its own engine (activation arena, graphs, stream): one "
                          "group's setup / VAE / host copies overlap the other's UNet forwards")
@@ -201,7 +207,9 @@ def main():
     K = args.steps
 
     from eta_inversion_b200.batching import run_lockstep, run_pipelined
+    from eta_inversion_b200.inversion.eta_inversion import EtaInversion
     from eta_inversion_b200.models import clone_pipeline
+    EtaInversion.skip_zero_weight_uncond = not args.reference_rows
     CB = max(1, args.cobatch)
     G = max(1, args.pipes)  # a step = G groups of CB edits, the groups of all steps are pipelined over G engines
     usd = syn.random_state_dict(syn.unet_param_spec(), 0)  # generated once, shared by the G engine instances
@@ -315,7 +323,7 @@ def main():
         return
     tf_peak, hbm_peak, peak_src = peaks()
     macs = flops.unet_macs_per_row()
-    rows = ROWS_PER_EDIT(args.inv_steps)
+    rows = ROWS_COMPUTED(args.inv_steps, not args.reference_rows)
     unet_ms = sum(v["ms"] for v in prof.values())
     # conv3x3 and the dense projections are ONE kernel (gemm_tc_k<T,BN,CONV>: the conv instantiation only differs in how the
     # TMA producer addresses the A operand), so they are accounted together as the dominant kernel
@@ -345,8 +353,15 @@ def main():
         "dtype": args.variant, "data": "synthetic",
         "config": bench_config(args.inv_steps),
         "engine": {"edits_per_step": CB * G,
-                   "cobatch": f"{CB} independent edits per GPU share each UNet forward (B={2 * CB} inversion, B={4 * CB} edit)",
+                   "cobatch": f"{CB} independent edits per GPU share each UNet forward (B={(2 if args.reference_rows else 1) * CB} "
+                              f"inversion, B={4 * CB} edit)",
                    "pipes": f"{G} lock-step group(s) in flight per GPU, each on its own engine handle (one shared copy of the weights)",
+                   "unet_rows_computed_per_edit": rows,
+                   "rows_note": ("the reference's etainv inversion always runs [uncond, cond] although guidance_scale_fwd = 1 gives the "
+                                 "unconditional row weight 0 (eta_inversion.py:319-328); the engine does not compute that row "
+                                 "(identical result; --reference-rows computes it)") if not args.reference_rows else
+                                "all rows the reference computes",
+                   "tflop_per_edit": round(2.0 * macs["total"] * rows / 1e12, 2),
                    "ms_per_unet_forward_avg": round(unet_graph_ms / (2 * args.inv_steps), 3),
                    "unet_share_of_step": round(unet_graph_ms / step_wall_ms, 3),
                    "parallelism": f"per-image sharding, {world} independent rank(s), no collective in the loop"},

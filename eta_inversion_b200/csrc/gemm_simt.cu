@@ -83,11 +83,14 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_k(Params p) {
     int n0 = blockIdx.x * BN;
     int ty = tid / 16, tx = tid % 16;  // 16x16 thread grid; thread owns rows ty*4+{0..3}, 64+ty*4+{0..3}; cols likewise
 
-    float acc[8][8];
+    // Two-level accumulation: `acc` sums at most 8 k-tiles (128 products) before it is folded into `tot`.  A single fp32
+    // running sum over K up to 23 040 drifts by ~sqrt(K) ulp per layer, which the 50 denoising steps of the parity tests
+    // amplify (error x ~15 from x_T to x_0); blocked summation keeps the parity path at the accuracy of the CPU BLAS.
+    float acc[8][8], tot[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 8; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.f; }
 
     float ra[8], rw[8];
     int nk = (p.K + BK - 1) / BK;
@@ -123,6 +126,12 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_k(Params p) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) { As[cur ^ 1][kb + j][r] = ra[j]; Ws[cur ^ 1][kb + j][r] = rw[j]; }
         }
+        if ((kt & 7) == 7 || kt + 1 == nk) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { tot[i][j] += acc[i][j]; acc[i][j] = 0.f; }
+        }
         __syncthreads();
     }
 
@@ -141,7 +150,7 @@ __global__ void __launch_bounds__(THREADS) gemm_simt_k(Params p) {
             float v[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                v[j] = acc[i][h * 4 + j];
+                v[j] = tot[i][h * 4 + j];
                 if (n + j < p.N) {
                     if (bias) v[j] += to_f<T>(bias[n + j]);
                     if (rb) v[j] += rb[n + j];

@@ -379,6 +379,28 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             stage16(piece + 1, h[4], h[5], h[6], h[7]);
                         } else {
                             uint32_t h[16];
+                            if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                                // bf16 keeps 8 mantissa bits: round ONCE, after bias and residual were added in fp32 (a bf16 ->
+                                // fp32 unpack is a shift / mask).  Three packed roundings per layer cost ~3 dB of image PSNR.
+                                float f[32];
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(r[i]);
+                                auto add_packed = [&](const uint4* q4) {
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const uint32_t w[4] = {q4[j].x, q4[j].y, q4[j].z, q4[j].w};
+#pragma unroll
+                                        for (int e = 0; e < 4; ++e) {
+                                            f[8 * j + 2 * e] += __uint_as_float(w[e] << 16);
+                                            f[8 * j + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+                                        }
+                                    }
+                                };
+                                if (brow) add_packed(b4);
+                                if (rrow) add_packed(r4);
+#pragma unroll
+                                for (int i = 0; i < 16; ++i) h[i] = pack2<T>(f[2 * i], f[2 * i + 1]);
+                            } else {
 #pragma unroll
                             for (int i = 0; i < 16; ++i) h[i] = pack2<T>(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
                             if (brow) {
@@ -394,6 +416,7 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                     h[4 * j] = add2<T>(h[4 * j], r4[j].x); h[4 * j + 1] = add2<T>(h[4 * j + 1], r4[j].y);
                                     h[4 * j + 2] = add2<T>(h[4 * j + 2], r4[j].z); h[4 * j + 3] = add2<T>(h[4 * j + 3], r4[j].w);
                                 }
+                            }
                             }
                             const int piece = cc >> 3;  // 32 output columns = 4 pieces
 #pragma unroll

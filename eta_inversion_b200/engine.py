@@ -58,6 +58,30 @@ class AttnControl:
     conv_inject_rows: int = 0
     _keep: list = field(default_factory=list, repr=False)
 
+    def drop_leading_rows(self, n: int) -> Optional["AttnControl"]:
+        """The same control for a batch whose first ``n`` rows were removed (rows renumbered), or None if the control
+        reads or writes one of those rows.  Used when the unconditional half of a CFG batch has weight exactly 0 and is
+        not computed (EtaInversion, guidance_scale_fwd == 1)."""
+        if self.conv_inject_rows:
+            return None
+        out = AttnControl(self_layer_mask=self.self_layer_mask, self_max_tokens=self.self_max_tokens, store_res=self.store_res,
+                          mapper=self.mapper, blend_a=self.blend_a, equalizer=self.equalizer, alpha_step=self.alpha_step,
+                          store_down=self.store_down, store_mid=self.store_mid, store_up=self.store_up)
+        if self.self_rows is not None:
+            kept = [r[n:] for r in self.self_rows]
+            if any(v < n for r in kept for v in r):
+                return None
+            out.self_rows = tuple([v - n for v in r] for r in kept)
+        if self.edit_pairs is not None:
+            if any(b < n or t < n for b, t in self.edit_pairs):
+                return None
+            out.edit_pairs = [(b - n, t - n) for b, t in self.edit_pairs]
+        if self.store_rows is not None:
+            if any(r < n for r in self.store_rows):
+                return None
+            out.store_rows = [r - n for r in self.store_rows]
+        return out
+
     def to_struct(self) -> EtaiAttnCtrl:
         s = EtaiAttnCtrl()
         self._keep = []

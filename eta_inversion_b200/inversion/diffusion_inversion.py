@@ -145,11 +145,23 @@ class DiffusionInversion:
         return text_embeddings.contiguous()
 
     # ---- UNet call -------------------------------------------------------------------------------
-    def _forward_unet(self, latent: torch.Tensor, t, context: torch.Tensor) -> torch.Tensor:
+    def _forward_unet(self, latent: torch.Tensor, t, context: torch.Tensor, zero_weight_uncond: bool = False) -> torch.Tensor:
+        """One UNet call with the step's attention control.  ``zero_weight_uncond``: ``latent`` holds the n latents of a
+        CFG batch whose unconditional half would be combined with weight exactly 0 (``context`` is the full [2n] context);
+        only the conditional rows are computed when the attention control does not touch the others -- the controllers
+        see the usual 2n-row batch -- and the result is the n conditional predictions.  Otherwise the full batch runs and
+        all 2n rows are returned."""
         B = latent.shape[0]
-        ctrl = self.controller.attn_control(self.unet, B)
+        Bc = 2 * B if zero_weight_uncond else B
+        ctrl = self.controller.attn_control(self.unet, Bc)
         for h in self.attn_hooks:
-            ctrl = merge_controls(ctrl, h.begin_forward(self.unet, B))
+            ctrl = merge_controls(ctrl, h.begin_forward(self.unet, Bc))
+        if zero_weight_uncond:
+            half = ctrl.drop_leading_rows(B) if ctrl is not None else None
+            if ctrl is None or half is not None:
+                ctrl, context = half, self._ctx_half(context, 1)
+            else:
+                latent = torch.cat([latent] * 2)
         latent = latent.float().contiguous()
         if self.unet_wrapper is not None:
             eps = self.unet_wrapper(self.unet, latent, t, context, control=ctrl)

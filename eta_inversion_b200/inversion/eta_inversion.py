@@ -165,13 +165,26 @@ class EtaInversion(DiffusionInversion):
             mask = torch.pow(mask, self.mask_mode_cfg["pow"])
         return mask
 
-    # ---- UNet call: always the full [uncond, cond] batch (eta_inversion.py:319-328) ---------------
+    # ---- UNet call ------------------------------------------------------------------------------------------------
+    # The reference always runs the full [uncond, cond] batch here (eta_inversion.py:319-328), also in the inversion loop
+    # where guidance_scale_fwd is 1 by default and the combine ``u + 1 * (c - u)`` gives the unconditional half weight 0:
+    # a third of an edit's UNet rows (50 x 1 of 50 x 2 + 50 x 4) is computed and discarded.  With ``skip_zero_weight_uncond``
+    # those rows are not computed (same result up to the rounding of ``u + (c - u)`` vs ``c``, ~1 ulp; the attention store
+    # only ever sees the conditional half, ptp.py:112-113).  Set it to False for the reference's exact row count.
+    skip_zero_weight_uncond = True
+
     def _unet_eps(self, latent, t, context, guidance_scale, is_fwd: bool = False):
-        latent_input = torch.cat([latent] * 2) if latent.shape[0] != context.shape[0] else latent
         if is_fwd:
             guidance_scale = self.guidance_scale_fwd
         if isinstance(guidance_scale, (tuple, list, dict, np.ndarray)):
             guidance_scale = guidance_scale[t.item()]
+        if (is_fwd and self.skip_zero_weight_uncond and float(guidance_scale) == 1.0
+                and context.shape[0] == 2 * latent.shape[0]):
+            eps = self._forward_unet(latent, t, context, zero_weight_uncond=True)
+            if eps.shape[0] == latent.shape[0]:
+                return eps, None  # conditional rows only: final
+            return eps, 1.0
+        latent_input = torch.cat([latent] * 2) if latent.shape[0] != context.shape[0] else latent
         return self._forward_unet(latent_input, t, context), float(guidance_scale)
 
     # ---- loop B step -----------------------------------------------------------------------------

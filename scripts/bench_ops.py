@@ -88,3 +88,15 @@ if "ln" in args.what:
         t = timeit(lambda i: E.layernorm(xs[i], g, b_), nv)
         by = 2.0 * B * HW * C * 2
         print(f"layernorm HW={HW} C={C} B={B}: {t * 1e6:8.1f} us  {by / t / 1e9:7.1f} GB/s algorithmic ({by / t / 1e9 / PB:.3f})")
+
+if "sched" in args.what:
+    # fused CFG + eta-DDIM step at a batched size: n latents of 4x64x64 fp32, eps rows [uncond.., cond..]
+    for n in (16, 256, 4096):
+        Eel = 4 * 64 * 64
+        eps = torch.randn(2 * n, Eel, device="cuda")
+        x = torch.randn(n, Eel, device="cuda")
+        eta_map = (torch.rand(Eel, device="cuda") > 0.5).float()
+        noise = torch.randn(1, Eel, device="cuda")
+        t = timeit(lambda i: E.cfg_ddim_step(eps, x, 0.5, 0.6, 7.5, 0.3, 0.1, eta_map, noise, None), 1)
+        by = (2 * n + n + n) * Eel * 4.0  # eps (2n rows) + x read, x' written
+        print(f"cfg_ddim_step n={n} latents: {t * 1e6:8.1f} us  {by / t / 1e9:7.1f} GB/s algorithmic ({by / t / 1e9 / PB:.3f} of HBM peak)")
