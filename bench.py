@@ -51,7 +51,7 @@ class ClockSampler:
     """nvidia-smi clocks + throttle reasons while the timed region runs."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, index: int):
         self.rows, self.proc, self.index = [], None, index
@@ -78,8 +78,11 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        util = [float(r[7]) for r in self.rows if len(r) >= 8 and r[7].replace(".", "").isdigit()]
+        power = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "gpu_util_pct_mean": round(statistics.mean(util), 1) if util else None,
+                "power_w_mean": round(statistics.mean(power), 1) if power else None}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -188,7 +191,7 @@ def main():
     ap.add_argument("--reference-rows", action="store_true", dest="reference_rows",
                     help="also compute the inversion's zero-weight unconditional rows, like the reference (300 instead of 250 "
                          "UNet rows per edit; same results)")
-    ap.add_argument("--pipes", type=int, default=2,
+    ap.add_argument("--pipes", type=int, default=3,
                     help="lock-step groups in flight per GPU, each on its own engine (activation arena, graphs, stream): one "
                          "group's setup / VAE / host copies overlap the other's UNet forwards")
     args = ap.parse_args()
@@ -340,10 +343,10 @@ def main():
                  for k, v in prof.items()}
     # DRAM traffic of the dominant kernel: one `ncu --set full` capture per round, kept under profiles/ (per launch)
     traffic_bytes, traffic_note = None, None
-    tpath = Path(__file__).resolve().parent / "profiles" / "r01_ncu_conv_traffic.json"
+    tpath = Path(__file__).resolve().parent / "profiles" / "r02_ncu_conv_traffic.json"
     if dom == "conv3x3" and tpath.exists():
         tj = json.loads(tpath.read_text())
-        traffic_bytes = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        traffic_bytes = int(tj["dram_bytes_read"] + tj["dram_bytes_write"])
         traffic_note = (f"{tj['launch']}: {traffic_bytes / 1e6:.1f} MB DRAM traffic vs {tj['algorithmic_bytes'] / 1e6:.1f} MB "
                         f"algorithmic (in + weights + out) in {tj['duration_us']} us under ncu; {tj['note']}")
     value = world * K * CB * G / (ms_total / 1e3)

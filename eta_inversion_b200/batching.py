@@ -49,6 +49,8 @@ class LockstepGroup:
         self._err: Optional[BaseException] = None
         self._aborted = False
         self._ctx_key, self._ctx_cat = None, None
+        self._table_cache: Dict[str, Any] = {}
+        self._store_cache = None
         self.forwards = 0
 
     def lane_unet(self, lane: int) -> _LaneUNet:
@@ -142,7 +144,15 @@ class LockstepGroup:
         if ed:
             out.edit_pairs = [(l * B + b, l * B + t) for l, c in ed for (b, t) in c.edit_pairs]
             for name in ("mapper", "blend_a", "equalizer", "alpha_step"):
-                setattr(out, name, torch.cat([getattr(c, name) for _, c in ed]).contiguous())
+                parts = [getattr(c, name) for _, c in ed]
+                # mapper / blend_a / equalizer are the same tensor objects for a whole loop: concatenate once, not per forward
+                # (the lanes' Python runs under one GIL, every op saved here is saved on the group's critical path)
+                key = (name, tuple((id(t), t._version) for t in parts))
+                hit = self._table_cache.get(name)
+                if hit is None or hit[0] != key:
+                    hit = (key, torch.cat(parts).contiguous(), parts)  # parts: strong references keep the ids valid
+                    self._table_cache[name] = hit
+                setattr(out, name, hit[1])
         # attention store: one combined accumulator per place, scattered back to the lanes' own tensors afterwards
         st = [(l, c) for l, c in enumerate(ctrls) if c is not None and c.store_rows is not None]
         if st:
@@ -152,17 +162,29 @@ class LockstepGroup:
             out.store_res = res.pop()
             out.store_rows = [l * B + r for l, c in st for r in c.store_rows]
             n = len(out.store_rows)
-            for place in ("store_down", "store_mid", "store_up"):
-                if any(getattr(c, place) is not None for _, c in st):
-                    acc = torch.zeros((n, out.store_res ** 2, 77), dtype=torch.float32, device=self.engine.device)
-                    setattr(out, place, acc)
-                    off = 0
-                    for _, c in st:
-                        m = len(c.store_rows)
-                        dst = getattr(c, place)
-                        if dst is not None:
-                            scatter.append(lambda dst=dst, acc=acc, off=off, m=m: dst.add_(acc[off:off + m]))
-                        off += m
+            places = [p for p in ("store_down", "store_mid", "store_up") if any(getattr(c, p) is not None for _, c in st)]
+            # one combined accumulator per place, kept across forwards and re-zeroed with ONE multi-tensor launch; the lanes'
+            # own accumulators receive their slices with ONE multi-tensor add after the forward (was: 3 allocations + memsets
+            # and one add per lane and place, 15 launches per forward for 4 lanes)
+            ckey = (n, out.store_res, tuple(places))
+            if self._store_cache is None or self._store_cache[0] != ckey:
+                self._store_cache = (ckey, [torch.zeros((n, out.store_res ** 2, 77), dtype=torch.float32,
+                                                        device=self.engine.device) for _ in places])
+            else:
+                torch._foreach_zero_(self._store_cache[1])
+            dsts, srcs = [], []
+            for place, acc in zip(places, self._store_cache[1]):
+                setattr(out, place, acc)
+                off = 0
+                for _, c in st:
+                    m = len(c.store_rows)
+                    dst = getattr(c, place)
+                    if dst is not None:
+                        dsts.append(dst)
+                        srcs.append(acc[off:off + m])
+                    off += m
+            if dsts:
+                scatter.append(lambda dsts=dsts, srcs=srcs: torch._foreach_add_(dsts, srcs))
         if any(c is not None and c.conv_inject_rows for c in ctrls):
             raise NotImplementedError("Plug-and-Play feature injection is not supported in lock-step groups")
         return out, scatter

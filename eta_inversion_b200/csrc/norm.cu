@@ -267,8 +267,119 @@ static bool groupnorm_cluster(const void* x, void* y, const void* gamma, const v
     return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Direct GroupNorm for the low-resolution layers (16-bit storage): one CTA per (batch row, group), two passes over the
+// group's HW x cpg elements (<= 123 KB: the second pass hits L1 / L2).  The cluster kernel above costs 13-24 us on these
+// shapes whatever their size (ncu, profiles/r02_ncu_shapes_summary.txt: 17.9 us for the 5 MB of 8x8x2560 at B = 16) --
+// cluster launch, cp.async slab and two cluster barriers are fixed latency; 30 of the UNet's 61 GroupNorms are this small.
+// Measured (ncu, B = 16): 8x8x2560 17.9 -> 7.1 us, 16x16x1280 13.4 -> 11.2 us; at 32x32 the cluster kernel is as fast or
+// faster (23.5 vs 22.4 us at C = 640, 50.6 vs 60.8 us at C = 1920), hence the HW <= 256 default.
+// Partition and reduction order depend on (HW, C) only: batch-invariant and deterministic like the other paths.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__device__ __forceinline__ void ldvec(const T* p, float (&v)[VEC]) {
+    if constexpr (VEC == 8) load8<T>(p, v);
+    else if constexpr (VEC == 4) load4<T>(p, v);
+    else { v[0] = to_f<T>(p[0]); v[1] = to_f<T>(p[1]); }
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void stvec(T* p, const float (&v)[VEC]) {
+    if constexpr (VEC == 8) store8<T>(p, v);
+    else if constexpr (VEC == 4) store4<T>(p, v);
+    else { Pack<T, 2> o; o.v[0] = from_f<T>(v[0]); o.v[1] = from_f<T>(v[1]); *reinterpret_cast<Pack<T, 2>*>(p) = o; }
+}
+
+template <typename T, int VEC, bool SILU>
+__global__ void __launch_bounds__(256) gn_direct_k(const T* __restrict__ x, T* __restrict__ y, const T* __restrict__ gamma,
+                                                   const T* __restrict__ beta, int HW, int C, int G, float eps) {
+    __shared__ double red[2][8];
+    __shared__ float s_mean, s_rstd;
+    const int b = blockIdx.y, g = blockIdx.x, cpg = C / G, vpr = cpg / VEC, nvec = HW * vpr;
+    const T* xb = x + (long)b * HW * C + g * cpg;
+    T* yb = y + (long)b * HW * C + g * cpg;
+    float s = 0.f, ss = 0.f;
+    for (int i0 = threadIdx.x; i0 < nvec; i0 += 4 * 256) {  // four independent loads in flight per thread
+        float v[4][VEC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 256, ic = i < nvec ? i : nvec - 1;
+            ldvec<T, VEC>(xb + (long)(ic / vpr) * C + (ic % vpr) * VEC, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + u * 256 < nvec) {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) { s += v[u][j]; ss = fmaf(v[u][j], v[u][j], ss); }
+            }
+        }
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = (double)s; red[1][warp] = (double)ss; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, aa = 0.0;
+        for (int w = 0; w < 8; ++w) { a += red[0][w]; aa += red[1][w]; }
+        const double n = (double)HW * cpg, mean = a / n;
+        double var = aa / n - mean * mean;
+        if (var < 0) var = 0;
+        s_mean = (float)mean;
+        s_rstd = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    const float mean = s_mean, rstd = s_rstd;
+    for (int i0 = threadIdx.x; i0 < nvec; i0 += 4 * 256) {
+        float v[4][VEC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 256, ic = i < nvec ? i : nvec - 1;
+            ldvec<T, VEC>(xb + (long)(ic / vpr) * C + (ic % vpr) * VEC, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 256;
+            if (i < nvec) {
+                const int c = (i % vpr) * VEC;
+                float ga[VEC], be[VEC], o[VEC];
+                ldvec<T, VEC>(gamma + g * cpg + c, ga);
+                ldvec<T, VEC>(beta + g * cpg + c, be);
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const float sc = rstd * ga[j];
+                    const float t = fmaf(v[u][j], sc, be[j] - mean * sc);
+                    o[j] = SILU ? silu_for<T>(t) : t;
+                }
+                stvec<T, VEC>(yb + (long)(i / vpr) * C + c, o);
+            }
+        }
+    }
+}
+
+static int gn_direct_max_hw() {
+    static const int v = [] { const char* e = getenv("ETAI_GN_DIRECT_MAX_HW"); return e ? atoi(e) : 256; }();
+    return v;
+}
+static bool gn_direct_ok(long HW, int C, int G, int dtype) {
+    return dtype != ETAI_F32 && HW <= gn_direct_max_hw() && C % G == 0 && (C / G) % 2 == 0 && G <= 65535;
+}
+template <typename T, bool SILU>
+static void gn_direct_launch(const void* x, void* y, const void* gamma, const void* beta, int B, long HW, int C, int G, float eps,
+                             cudaStream_t s) {
+    const int cpg = C / G;
+    dim3 grid(G, B);
+#define GND(V) gn_direct_k<T, V, SILU><<<grid, 256, 0, s>>>((const T*)x, (T*)y, (const T*)gamma, (const T*)beta, (int)HW, C, G, eps)
+    if (cpg % 8 == 0) GND(8);
+    else if (cpg % 4 == 0) GND(4);
+    else GND(2);
+#undef GND
+    KERNEL_CHECK();
+}
+
 int groupnorm_launches(long HW, int C, int groups, int dtype) {
     static const bool disabled = [] { const char* e = getenv("ETAI_GN_TWO_PASS"); return e && e[0] == '1'; }();
+    if (gn_direct_ok(HW, C, groups, dtype)) return 1;
     if (disabled || C % 8 || C % groups) return 2;
     return gn_cluster_plan(HW, C, groups, dtype_size(dtype)).ok ? 1 : 2;
 }
@@ -478,6 +589,17 @@ void groupnorm(const void* x, void* y, const void* gamma, const void* beta, int 
     ETAI_CHECK(C % 8 == 0 && C % groups == 0 && groups <= 64, ETAI_ERR_ARG, "groupnorm: C%8, C%groups, groups<=64");
     ETAI_CHECK(C / 8 <= 512, ETAI_ERR_ARG, "groupnorm: C too large");
     ETAI_CHECK(ws != nullptr, ETAI_ERR_ARG, "groupnorm: workspace required");
+    if (gn_direct_ok(HW, C, groups, dtype)) {
+        ETAI_CHECK(B <= 65535, ETAI_ERR_ARG, "groupnorm: B too large");
+        if (dtype == ETAI_F16) {
+            if (silu) gn_direct_launch<__half, true>(x, y, gamma, beta, B, HW, C, groups, eps, s);
+            else gn_direct_launch<__half, false>(x, y, gamma, beta, B, HW, C, groups, eps, s);
+        } else {
+            if (silu) gn_direct_launch<__nv_bfloat16, true>(x, y, gamma, beta, B, HW, C, groups, eps, s);
+            else gn_direct_launch<__nv_bfloat16, false>(x, y, gamma, beta, B, HW, C, groups, eps, s);
+        }
+        return;
+    }
     if (groupnorm_cluster(x, y, gamma, beta, B, HW, C, groups, eps, silu, dtype, s)) return;
     GnPlan p = gn_plan(HW, C);
     size_t smem = (size_t)2 * p.R * C * sizeof(float);

@@ -106,11 +106,17 @@ class DDIMScheduler:
             m = getattr(eta, "eta", eta)
             eta_map = torch.broadcast_to(m.float(), (1,) + tuple(sample.shape[1:])).contiguous()  # shared by all rows
             eta_s = 1.0
-        if float(eta_s) > 0 and variance_noise is None:
-            variance_noise = torch.randn(sample.shape[1:], generator=generator, device=sample.device, dtype=torch.float32)[None]
+        if float(eta_s) > 0 and variance_noise is None:  # diffusers: randn of model_output.shape, every row its own noise
+            variance_noise = torch.randn(sample.shape, generator=generator, device=sample.device, dtype=torch.float32)
+        eps, x = model_output.float().contiguous(), sample.float().contiguous()
+        B = x.shape[0]
+        if variance_noise is not None and variance_noise.shape[0] == B and B > 1:
+            # the fused kernel applies ONE noise tensor to all rows (the eta-inversion loop shares it); per-row noise = per-row calls
+            rows = [self.fused_step(eps[i:i + 1].contiguous(), timestep, x[i:i + 1].contiguous(), None, float(eta_s), eta_map,
+                                    variance_noise[i].reshape(1, -1).float().contiguous())[0] for i in range(B)]
+            return DDIMSchedulerOutput(torch.cat(rows).to(sample.dtype), None)
         cand = None if variance_noise is None else variance_noise.reshape(1, -1).float().contiguous()
-        prev, _ = self.fused_step(model_output.float().contiguous(), timestep, sample.float().contiguous(), None,
-                                  float(eta_s), eta_map, cand)
+        prev, _ = self.fused_step(eps, timestep, x, None, float(eta_s), eta_map, cand)
         return DDIMSchedulerOutput(prev.to(sample.dtype), None)
 
 

@@ -34,7 +34,7 @@ class ControllerAttentionStorePerStep(PromptToPromptControllerAttentionStore):
         # one token per word; a repeated word resolves to its FIRST occurrence (ptp_editor.py:72, list.index)
         idx = [words.index(w) + 1 for w in words]
         maps = self.get_attention_maps(idx, res=self.res, from_where=self.from_where, resize=64)
-        self.callback([maps[i] for i in range(len(words))], t)  # per word [1,64,64]
+        self.callback(maps, t)  # [words,1,64,64]: maps[w] is the reference's per-word [1,64,64] entry (no per-word slicing ops)
         return super().end_step(latent, noise_pred, t)
 
 
@@ -85,6 +85,7 @@ class EtaInversion(DiffusionInversion):
         self.noise_device = noise_device
         self.noise_provider = None  # optional callable(step_index) -> [K,1,4,64,64]; default = seeded generator
         self.picks: list = []       # picked candidate index of every denoise step of the last loop (device tensors)
+        self._loop_cache = None     # per-loop cache of step-independent tensors (set by diffusion_backward)
 
     # ---- noise -----------------------------------------------------------------------------------
     def sample_variance_noise(self, n: int, generator: Optional[torch.Generator] = None) -> torch.Tensor:
@@ -215,10 +216,17 @@ class EtaInversion(DiffusionInversion):
         eta_map = None
         delta_mask = None
         if self.mask_mode_cfg is not None:
-            m = self.get_mask("mask_eta", mask, t, edit_word_idx)
+            # "gt" / "fwd_mean" masks do not depend on the step: thresholded and broadcast once per loop, not once per step
+            static = self.mask_mode_cfg["mask_eta"] in ("gt", "fwd_mean") and self._loop_cache is not None
+            if static and "eta_map" in self._loop_cache:
+                eta_map = self._loop_cache["eta_map"]
+            else:
+                m = self.get_mask("mask_eta", mask, t, edit_word_idx)
+                if m is not None:
+                    eta_map = torch.broadcast_to(m.float(), (1,) + tuple(latent.shape[1:])).contiguous()
+                if static:
+                    self._loop_cache["eta_map"] = eta_map
             delta_mask = self.get_mask("mask_dirinv", mask, t, edit_word_idx)
-            if m is not None:
-                eta_map = torch.broadcast_to(m.float(), (1,) + tuple(latent.shape[1:])).contiguous()
         leak = self.mask_mode_cfg["target_dirinv"] if self.mask_mode_cfg is not None else None
         if leak is None:
             new_latent, noise_pred = E.cfg_ddim_step(eps_raw, latent, a_t, a_p, g, eta, var, eta_map, cand, losses,
@@ -243,10 +251,14 @@ class EtaInversion(DiffusionInversion):
         steps = self.scheduler_bwd.timesteps
         noise = self._noise_for_loop(len(steps))
         self.picks = []
-        for i, t in enumerate(self.pbar(steps, desc="backward")):
-            latent, noise_pred = self.predict_step_backward(
-                latent, t, context, source_latent_prev=inv_result["latents"][-(i + 2)], mask=mask,
-                edit_word_idx=edit_word_idx, noise_cand=noise[i])
+        self._loop_cache = {}
+        try:
+            for i, t in enumerate(self.pbar(steps, desc="backward")):
+                latent, noise_pred = self.predict_step_backward(
+                    latent, t, context, source_latent_prev=inv_result["latents"][-(i + 2)], mask=mask,
+                    edit_word_idx=edit_word_idx, noise_cand=noise[i])
+        finally:
+            self._loop_cache = None
         return latent
 
     # ---- loop A ----------------------------------------------------------------------------------
@@ -263,6 +275,6 @@ class EtaInversion(DiffusionInversion):
         with self.use_controller(store):
             fwd_result = super().invert(image, prompt, context, guidance_scale_fwd, inv_cfg=inv_cfg)
         per_step = list(self.attn_maps_forward.values())
-        self.attn_maps_forward["mean"] = [torch.mean(torch.stack([a[w] for a in per_step]), dim=0)
-                                          for w in range(len(per_step[0]))]
+        # mean over the steps for every word at once ([words,1,64,64]; indexing [w] gives the reference's per-word list entry)
+        self.attn_maps_forward["mean"] = torch.mean(torch.stack(per_step), dim=0)
         return fwd_result

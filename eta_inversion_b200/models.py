@@ -58,9 +58,10 @@ class StablePostProc:
     """VAE output -> uint8 HWC array of the first image."""
 
     def __call__(self, image: torch.Tensor) -> np.ndarray:
-        image = (image.float() / 2 + 0.5).clamp(0, 1)
-        image = image.cpu().permute(0, 2, 3, 1).numpy()
-        return (image * 255).astype(np.uint8)[0]
+        # same arithmetic and truncation as the reference ((x/2+0.5).clamp(0,1) * 255 -> uint8), done on the image's device so
+        # that only the first image's HWC uint8 bytes cross PCIe (the reference moves the fp32 NCHW batch and converts on the host)
+        image = ((image[:1].float() / 2 + 0.5).clamp(0, 1) * 255).to(torch.uint8)
+        return image.permute(0, 2, 3, 1).contiguous().cpu().numpy()[0]
 
 
 class SyntheticTokenizer:

@@ -168,6 +168,8 @@ class AttentionControlEdit(AttentionStore):
         alpha_host = ptp_utils.get_time_words_attention_alpha(prompts, num_steps, cross_replace_steps, model.tokenizer)
         self._alpha_active = [bool(a.any()) for a in alpha_host]  # host copy: skip the edit when a step's alpha is all 0
         self.cross_replace_alpha = h2d(alpha_host, model.device)
+        # per-step [1,77] fp32 rows, sliced once (begin_forward runs under the lanes' shared GIL every step)
+        self._alpha_rows = list(self.cross_replace_alpha.reshape(len(alpha_host), 1, MAX_NUM_WORDS).float().contiguous().unbind(0))
         if type(self_replace_steps) is float:
             self_replace_steps = 0, self_replace_steps
         self.num_self_replace = int(num_steps * self_replace_steps[0]), int(num_steps * self_replace_steps[1])
@@ -195,7 +197,7 @@ class AttentionControlEdit(AttentionStore):
         if self._alpha_active[self.cur_step]:  # alpha == 0 for every word leaves P_tgt untouched (ptp.py:209-210)
             ctrl.edit_pairs = [(src, tgt)]
             ctrl.mapper, ctrl.blend_a, ctrl.equalizer = mapper.contiguous(), blend_a.contiguous(), eq.contiguous()
-            ctrl.alpha_step = self.cross_replace_alpha[self.cur_step].reshape(1, MAX_NUM_WORDS).float().contiguous()
+            ctrl.alpha_step = self._alpha_rows[self.cur_step]
         if self.num_self_replace[0] <= self.cur_step < self.num_self_replace[1]:
             rows = list(range(batch_rows))
             qk = list(rows)

@@ -13,6 +13,7 @@ The only dataset on this box is the synthetic PIE-shaped one (`data: [{type: syn
 from __future__ import annotations
 
 import argparse
+import time
 import itertools
 import os
 from pathlib import Path
@@ -142,8 +143,15 @@ def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int, pipes: i
 
         def run_group(idx):
             return run_groups([idx])[0]
+        if world > 1:
+            dist.barrier()
+        t_sweep = time.perf_counter()
         records = run_sweep(n, rank, world, cobatch, run_group, window=4 * len(all_pipes), run_groups=run_groups)
+        t_sweep = time.perf_counter() - t_sweep  # includes the final gather = the slowest rank
         if rank == 0:
+            done = sum(r['status'] == 'done' for r in records)
+            print(f"combo {ci}: {done} edits in {t_sweep:.1f} s on {world} GPU(s) = {done / max(t_sweep, 1e-9):.2f} edits/s "
+                  f"(first-call graph capture, VAE / CLIP, PNG encode + write included; model load excluded)")
             (out_dir.parent / "records.yaml").write_text(yaml.safe_dump(records))
             print(f"combo {ci}: {sum(r['status'] == 'done' for r in records)} edited, "
                   f"{sum(r['status'] == 'skipped' for r in records)} skipped -> {out_dir}")

@@ -27,6 +27,7 @@ pipe, _ = etai.load_diffusion_model("synthetic-sd15", "cuda:0", variant="fp16", 
 pipe.cache_text_embeddings = False
 imgs = [syn.synthetic_image(i).cuda() for i in range(CB)]
 profs = []
+CPU = []
 PROFILE = [False]
 
 
@@ -35,6 +36,14 @@ class Wrapped:
         self.ed = ed
 
     def edit(self, **kw):
+        import threading as _th
+        c0 = time.thread_time()
+        try:
+            return self._edit(**kw)
+        finally:
+            CPU.append(time.thread_time() - c0)
+
+    def _edit(self, **kw):
         import threading as _th
         if not PROFILE[0] or _th.current_thread().name != "etai-lane-0":  # one profiler may be active per process
             return self.ed.edit(**kw)
@@ -65,6 +74,8 @@ pipe.unet.time_forwards(True)
 t0 = time.perf_counter(); group(); t1 = time.perf_counter()
 unet_ms = pipe.unet.time_forwards(False)
 print(f"group wall {1e3 * (t1 - t0):.1f} ms, UNet forwards {unet_ms:.1f} ms ({unet_ms / (1e3 * (t1 - t0)):.3f})")
+print(f"CPU time (time.thread_time) of the lane threads for that group: {[round(1e3 * c) for c in CPU[-CB:]]} ms, sum "
+      f"{1e3 * sum(CPU[-CB:]):.0f} ms -- all of it serialised by the GIL")
 PROFILE[0] = True
 t0 = time.perf_counter(); group(); t1 = time.perf_counter()
 print(f"profiled group wall {1e3 * (t1 - t0):.1f} ms")

@@ -169,3 +169,46 @@ def test_ddpm_and_edict_inverse_schedulers_match_reference():
         for i, t in enumerate(bwd.timesteps):
             x = bwd.step(eps[(steps - 1 - i) % 6], t, x).prev_sample
             assert np.abs(x.numpy() - gold[f"edict_s{steps}_bwd"][i]).max() < 2e-5 * max(1.0, float(x.abs().max()))
+
+
+def test_attn_control_drop_leading_rows():
+    """AttnControl.drop_leading_rows: the control of a CFG batch whose unconditional half is not computed (EtaInversion at
+    guidance_scale_fwd == 1) -- rows renumbered, None when the control reads or writes a dropped row."""
+    from eta_inversion_b200.engine import AttnControl
+    store = AttnControl(store_rows=[2, 3], store_res=16)
+    half = store.drop_leading_rows(2)
+    assert half.store_rows == [0, 1] and half.store_res == 16 and half.self_rows is None and half.edit_pairs is None
+    assert AttnControl(store_rows=[1, 3]).drop_leading_rows(2) is None            # stores an unconditional row
+    remap = AttnControl(self_rows=([0, 1, 2, 2], [0, 1, 2, 2], [0, 1, 2, 3]), self_layer_mask=0xFF, self_max_tokens=256)
+    h = remap.drop_leading_rows(2)
+    assert h.self_rows == ([0, 0], [0, 0], [0, 1]) and h.self_layer_mask == 0xFF and h.self_max_tokens == 256
+    masa = AttnControl(self_rows=([0, 1, 2, 3], [0, 0, 2, 2], [0, 0, 2, 2]))      # MasaCtrl: rows of each half read the half's source
+    assert masa.drop_leading_rows(2).self_rows == ([0, 1], [0, 0], [0, 0])
+    assert AttnControl(self_rows=([0, 1, 0, 1], [0, 1, 2, 3], [0, 1, 2, 3])).drop_leading_rows(2) is None  # reads a dropped row
+    assert AttnControl(edit_pairs=[(2, 3)]).drop_leading_rows(2).edit_pairs == [(0, 1)]
+    assert AttnControl(edit_pairs=[(0, 3)]).drop_leading_rows(2) is None
+    assert AttnControl(conv_inject_rows=1).drop_leading_rows(1) is None
+
+
+def test_null_text_loss_gradient_closed_form():
+    """The closed-form dL/d(eps_uncond) NullTextInversion feeds to etai_unet_backward_ctx equals torch autograd through the
+    reference's own arithmetic: CFG combine, DDIMScheduler.step (eta = 0), mse_loss (null_text_inversion.py:72-76)."""
+    from oracle import sd15
+    sch = sd15.sd_scheduler()
+    sch.set_timesteps(10)
+    g = torch.Generator().manual_seed(3)
+    x, e_c, target = (torch.randn((1, 4, 64, 64), generator=g) for _ in range(3))
+    e_u = torch.randn((1, 4, 64, 64), generator=g).requires_grad_(True)
+    gs = 7.5
+    for t in (sch.timesteps[0], sch.timesteps[4], sch.timesteps[-1]):
+        e_u.grad = None
+        eps = e_u + gs * (e_c - e_u)
+        rec = sch.step(eps, t, x).prev_sample
+        loss = torch.nn.functional.mse_loss(rec, target)
+        loss.backward()
+        a_t = float(sch.alphas_cumprod[int(t)])
+        p = int(t) - sch.config.num_train_timesteps // sch.num_inference_steps
+        a_p = float(sch.alphas_cumprod[p]) if p >= 0 else float(sch.final_alpha_cumprod)
+        coef = (1.0 - gs) * ((1.0 - a_p) ** 0.5 - (a_p ** 0.5) * ((1.0 - a_t) ** 0.5) / (a_t ** 0.5))
+        closed = (rec.detach() - target) * (2.0 * coef / rec.numel())
+        assert torch.allclose(e_u.grad, closed, rtol=2e-4, atol=1e-12), float((e_u.grad - closed).abs().max())

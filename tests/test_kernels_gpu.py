@@ -308,6 +308,27 @@ def test_scheduler_step_matches_closed_form():
     assert (back - x).abs().max().item() < 1e-4
 
 
+def test_ddim_step_stochastic_rows_get_independent_noise():
+    """DDIMScheduler.step(eta > 0, variance_noise=None) with B > 1: diffusers draws randn of the SAMPLE's shape, so every row
+    has its own noise; an explicit per-row variance_noise [B,C,H,W] is honoured row by row."""
+    from eta_inversion_b200.models import sd_scheduler
+    sch = sd_scheduler()
+    sch.set_timesteps(10)
+    t = sch.timesteps[3]
+    x, eps = _rand((2, 4, 64, 64), 7).cuda(), _rand((2, 4, 64, 64), 8).cuda()
+    eps[1], x[1] = eps[0], x[0]  # identical rows: any difference in the output is the noise
+    g = torch.Generator(device="cuda").manual_seed(0)
+    out = sch.step(eps, t, x, eta=1.0, generator=g).prev_sample
+    assert (out[0] - out[1]).abs().max().item() > 1e-2
+    noise = _rand((2, 4, 64, 64), 9).cuda()
+    o2 = sch.step(eps, t, x, eta=1.0, variance_noise=noise).prev_sample
+    a_t, a_p = sch.alpha(int(t)), sch.alpha(sch.prev_timestep(t))
+    sig = float(sch._get_variance(int(t), sch.prev_timestep(t))) ** 0.5
+    x0 = (x - math.sqrt(1 - a_t) * eps) / math.sqrt(a_t)
+    ref = math.sqrt(a_p) * x0 + math.sqrt(max(1 - a_p - sig ** 2, 0.0)) * eps + sig * noise
+    assert (o2 - ref).abs().max().item() < 1e-4
+
+
 def test_errors_are_loud():
     from eta_inversion_b200 import engine as E
     with pytest.raises(RuntimeError):
