@@ -261,8 +261,8 @@ def main():
                 for grp in groups]
         return run_pipelined(pipes, jobs, make_editor, on_result=on_result)
 
-    def launches_now():
-        return sum(p.unet.launch_count for p in pipes) + E.LAUNCHES[0]
+    def launches_now():  # UNet handles + the shared VAE / CLIP handles + the op-level entry points (scheduler step, noise losses)
+        return (sum(p.unet.launch_count for p in pipes) + pipe.vae.launch_count + pipe.text_encoder.launch_count + E.LAUNCHES[0])
 
     # ---- (1) device-resident throughput ----------------------------------------------------------
     steps(dev_imgs, 0, W)

@@ -649,6 +649,64 @@ __global__ void cross_bwd_fold_k(const float* __restrict__ part, float* __restri
     dkv[r * ld_dkv + kv_off + col] = a;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// helpers of the GEMM-based self-attention backward (see etai_unet::self_attention_bwd_gemm)
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void attn_pack_heads_k(const T* __restrict__ src, long ld, int N, int heads, int d, int DP, T* __restrict__ dst,
+                                  T* __restrict__ dstT, long total) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;  // over heads * N * DP
+    if (i >= total) return;
+    const int c = (int)(i % DP);
+    const long r = (i / DP) % N;
+    const int h = (int)(i / ((long)DP * N));
+    const T v = c < d ? src[r * ld + h * d + c] : from_f<T>(0.f);
+    dst[i] = v;
+    if (dstT) dstT[((long)h * DP + c) * N + r] = v;
+}
+template <typename T>
+__global__ void attn_unpack_heads_k(const T* __restrict__ src, int N, int heads, int d, int DP, T* __restrict__ dst, long ld,
+                                    long total) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;  // over heads * N * d
+    if (i >= total) return;
+    const int c = (int)(i % d);
+    const long r = (i / d) % N;
+    const int h = (int)(i / ((long)d * N));
+    dst[r * ld + h * d + c] = src[((long)h * N + r) * DP + c];
+}
+template <typename T>
+__global__ void attn_rowdot_k(const T* __restrict__ a, long lda, const T* __restrict__ b, long ldb, int N, int heads, int d,
+                              float* __restrict__ out) {
+    const long w = blockIdx.x * (long)(blockDim.x >> 5) + (threadIdx.x >> 5);  // one warp per (head, row)
+    const int lane = threadIdx.x & 31;
+    if (w >= (long)heads * N) return;
+    const int h = (int)(w / N);
+    const long r = w % N;
+    float acc = 0.f;
+    for (int c = lane; c < d; c += 32) acc += to_f<T>(a[r * lda + h * d + c]) * to_f<T>(b[r * ldb + h * d + c]);
+    acc = warp_sum(acc);
+    if (lane == 0) out[w] = acc;
+}
+template <typename T, int MODE>
+__global__ void attn_bwd_elementwise_k(T* __restrict__ x, const T* __restrict__ p, const float* __restrict__ vec, int cols,
+                                       float scale, long nvec) {
+    long i = blockIdx.x * (long)blockDim.x + threadIdx.x;  // over rows * cols / 8
+    if (i >= nvec) return;
+    const long e = i * 8;
+    const int row = (int)(e / cols), col = (int)(e % cols);
+    float v[8], pv[8];
+    load8<T>(x + e, v);
+    if (MODE != 1) load8<T>(p + e, pv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (MODE == 0) v[j] = pv[j] * (v[j] - vec[row]) * scale;
+        else if (MODE == 1) v[j] = __expf(v[j] * scale - vec[col + j]);
+        else v[j] = pv[j] * (v[j] - vec[col + j]) * scale;
+    }
+    store8<T>(x + e, v);
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -718,6 +776,36 @@ void layernorm_bwd(const void* x, const void* dy, const void* gamma, void* dx, l
                    cudaStream_t s) {
     ETAI_DISPATCH_DTYPE(dtype, T, (ln_bwd_k<T><<<cdiv(M, 8), 256, 0, s>>>((const T*)x, (const T*)dy, (const T*)gamma, (T*)dx, M, C,
                                                                         eps)));
+    KERNEL_CHECK();
+}
+
+
+void attn_pack_heads(const void* src, long ld, int N, int heads, int d, int DP, void* dst, void* dstT, int dtype, cudaStream_t s) {
+    long total = (long)heads * N * DP;
+    ETAI_DISPATCH_DTYPE(dtype, T, (attn_pack_heads_k<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)src, ld, N, heads, d, DP, (T*)dst,
+                                                                                     (T*)dstT, total)));
+    KERNEL_CHECK();
+}
+void attn_unpack_heads(const void* src, int N, int heads, int d, int DP, void* dst, long ld, int dtype, cudaStream_t s) {
+    long total = (long)heads * N * d;
+    ETAI_DISPATCH_DTYPE(dtype, T, (attn_unpack_heads_k<T><<<cdiv(total, 256), 256, 0, s>>>((const T*)src, N, heads, d, DP, (T*)dst, ld,
+                                                                                       total)));
+    KERNEL_CHECK();
+}
+void attn_rowdot(const void* a, long lda, const void* b, long ldb, int N, int heads, int d, float* out, int dtype, cudaStream_t s) {
+    long warps = (long)heads * N;
+    ETAI_DISPATCH_DTYPE(dtype, T, (attn_rowdot_k<T><<<cdiv(warps, 8), 256, 0, s>>>((const T*)a, lda, (const T*)b, ldb, N, heads, d, out)));
+    KERNEL_CHECK();
+}
+void attn_bwd_elementwise(void* x, const void* p, const float* vec, int rows, int cols, float scale, int mode, int dtype,
+                          cudaStream_t s) {
+    ETAI_CHECK(cols % 8 == 0 && mode >= 0 && mode <= 2, ETAI_ERR_ARG, "attn_bwd_elementwise: cols%8, mode");
+    long nvec = (long)rows * cols / 8;
+    ETAI_DISPATCH_DTYPE(dtype, T, {
+        if (mode == 0) attn_bwd_elementwise_k<T, 0><<<cdiv(nvec, 256), 256, 0, s>>>((T*)x, (const T*)p, vec, cols, scale, nvec);
+        else if (mode == 1) attn_bwd_elementwise_k<T, 1><<<cdiv(nvec, 256), 256, 0, s>>>((T*)x, (const T*)p, vec, cols, scale, nvec);
+        else attn_bwd_elementwise_k<T, 2><<<cdiv(nvec, 256), 256, 0, s>>>((T*)x, (const T*)p, vec, cols, scale, nvec);
+    });
     KERNEL_CHECK();
 }
 

@@ -107,7 +107,8 @@ void pack_conv_weight(const float* oihw, void* out, int O, int I, int Opad, int 
 void pack_geglu_weight(const float* w, const float* b, void* wout, void* bout, int N2, int K, int dtype, cudaStream_t s);
 
 // ---------------- VAE / CLIP text tower only (textvae_ops.cu) -----------------------------------
-void softmax_rows(void* x, long rows, int n, float scale, int dtype, cudaStream_t s);  // in place, softmax(scale*x) per row
+// in place, softmax(scale*x) per row; lse (optional): fp32 [rows] log-sum-exp of the scaled row
+void softmax_rows(void* x, long rows, int n, float scale, int dtype, cudaStream_t s, float* lse = nullptr);
 void clip_embed(const int* ids, const void* tok, const void* pos, void* out, long rows, int L, int C, int vocab, int dtype,
                 cudaStream_t s);
 void quick_gelu(void* x, long n, int dtype, cudaStream_t s);                            // in place, x*sigmoid(1.702x)
@@ -148,6 +149,16 @@ struct CrossAttnBwdArgs {
     float scale;
     int dtype;
 };
+// ---- pieces of the GEMM-based self-attention backward (16-bit engines, N >= 1024): every N x N product runs on gemm_tc_k
+// head slices [N, d] (row stride ld) -> zero-padded [heads][N][DP] and its transpose [heads][DP][N] (dstT may be null)
+void attn_pack_heads(const void* src, long ld, int N, int heads, int d, int DP, void* dst, void* dstT, int dtype, cudaStream_t s);
+void attn_unpack_heads(const void* src, int N, int heads, int d, int DP, void* dst, long ld, int dtype, cudaStream_t s);
+void attn_rowdot(const void* a, long lda, const void* b, long ldb, int N, int heads, int d, float* out, int dtype, cudaStream_t s);
+// mode 0: x = p * (x - dsum[row]) * scale          (dS   from dP,   p = P   [row = query])
+// mode 1: x = exp(x * scale - lse[col])             (P^T  from S^T,  columns = queries)
+// mode 2: x = p * (x - dsum[col]) * scale          (dS^T from dP^T, p = P^T)
+void attn_bwd_elementwise(void* x, const void* p, const float* vec, int rows, int cols, float scale, int mode, int dtype,
+                          cudaStream_t s);
 size_t cross_attention_bwd_partial_bytes(int B, int N, int L, int C, int d);
 void cross_attention_bwd(const CrossAttnBwdArgs& a, cudaStream_t s);
 

@@ -24,7 +24,7 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* sm) {
 
 // one CTA per row; the row is kept in registers (n <= 256 threads * 8 * PER)
 template <typename T, int PER>
-__global__ void __launch_bounds__(256) softmax_rows_k(T* __restrict__ x, int n, float scale) {
+__global__ void __launch_bounds__(256) softmax_rows_k(T* __restrict__ x, int n, float scale, float* __restrict__ lse) {
     __shared__ float sm[8];
     T* row = x + (long)blockIdx.x * n;
     float v[PER][8];
@@ -49,6 +49,7 @@ __global__ void __launch_bounds__(256) softmax_rows_k(T* __restrict__ x, int n, 
         }
     }
     sum = block_reduce(sum, false, sm);
+    if (lse && threadIdx.x == 0) lse[blockIdx.x] = mx + __logf(sum);  // log-sum-exp of the scaled row (attention backward)
     const float inv = 1.0f / sum;
 #pragma unroll
     for (int p = 0; p < PER; ++p) {
@@ -149,13 +150,13 @@ __global__ void __launch_bounds__(256) clip_attention_k(const T* __restrict__ qk
 
 }  // namespace
 
-void softmax_rows(void* x, long rows, int n, float scale, int dtype, cudaStream_t s) {
+void softmax_rows(void* x, long rows, int n, float scale, int dtype, cudaStream_t s, float* lse) {
     ETAI_CHECK(n % 8 == 0 && n <= 256 * 8 * 4, ETAI_ERR_ARG, "softmax_rows: n%8==0 and n<=8192");
     ETAI_CHECK(rows >= 1 && rows < (1L << 31), ETAI_ERR_ARG, "softmax_rows: rows");
     ETAI_DISPATCH_DTYPE(dtype, T, {
-        if (n <= 2048) softmax_rows_k<T, 1><<<(unsigned)rows, 256, 0, s>>>((T*)x, n, scale);
-        else if (n <= 4096) softmax_rows_k<T, 2><<<(unsigned)rows, 256, 0, s>>>((T*)x, n, scale);
-        else softmax_rows_k<T, 4><<<(unsigned)rows, 256, 0, s>>>((T*)x, n, scale);
+        if (n <= 2048) softmax_rows_k<T, 1><<<(unsigned)rows, 256, 0, s>>>((T*)x, n, scale, lse);
+        else if (n <= 4096) softmax_rows_k<T, 2><<<(unsigned)rows, 256, 0, s>>>((T*)x, n, scale, lse);
+        else softmax_rows_k<T, 4><<<(unsigned)rows, 256, 0, s>>>((T*)x, n, scale, lse);
     });
     KERNEL_CHECK();
 }

@@ -141,6 +141,7 @@ struct etai_unet : etai::OpCtx {
     void enable_backward(int max_batch);
     void* make_wT(const void* w, int n, int k, bool conv);
     void backward_walk(int B, cudaStream_t s);
+    void self_attention_bwd_gemm(const TapeRec& r, const void* dy, char* dqkv, bool plan, cudaStream_t s);
     void backward_ctx(const float* d_eps, int B, float* d_ctx, cudaStream_t user);
 
     void build(const etai_tensor* weights, int n_weights);
@@ -736,7 +737,12 @@ void etai_unet::backward_walk(int B, cudaStream_t s) {
             const int C = r.C;
             const long M = (long)r.B * r.HW;
             char* dqkv = (char*)garena.alloc((size_t)M * 3 * C * esz);
-            if (!plan) {
+            static const bool simt_only = [] { const char* e = getenv("ETAI_ATTN_BWD_SIMT"); return e && e[0] == '1'; }();
+            if (tc && r.HW >= 1024 && !simt_only) {
+                const size_t mark = garena.off;
+                self_attention_bwd_gemm(r, dy, dqkv, plan, s);
+                garena.off = mark;  // the per-layer scratch is dead once the layer's kernels are enqueued (stream order)
+            } else if (!plan) {
                 SelfAttnBwdArgs a;
                 const char* qkv = (const char*)r.x;
                 a.q = qkv; a.k = qkv + (size_t)C * esz; a.v = qkv + (size_t)2 * C * esz; a.o = r.y; a.dout = dy;
@@ -812,6 +818,67 @@ void etai_unet::backward_walk(int B, cudaStream_t s) {
         b.A = dkv_t; b.W = make_wT(kv_all.w, kv_all.n, kv_all.k, false); b.C = bwd_dctx;
         b.M = Mc; b.N = cfg.cross_dim; b.K = kv_total; b.lda = kv_total; b.ldc = cfg.cross_dim; b.ldr = cfg.cross_dim;
         gemm(b, s);
+    }
+}
+
+
+// Self-attention backward of one layer with every N x N product on the tensor-core GEMM kernel (16-bit engines, N >= 1024;
+// the SIMT flash-style kernels of backward.cu stay the fp32 parity path and serve the short sequences).  Per head, with
+// Qp / Kp / Vp / dOp the head's [N, DP] zero-padded slices and XpT their transposes:
+//   P    = softmax(scale Qp Kp^T) (+ lse)     dP   = dOp Vp^T       dS   = P   o (dP   - D[row]) scale      dQ = dS   Kp
+//   P^T  = exp(scale Kp Qp^T - lse[col])      dP^T = Vp dOp^T       dS^T = P^T o (dP^T - D[col]) scale      dK = dS^T Qp
+//                                                                                                          dV = P^T  dOp
+// Seven GEMMs and four elementwise passes over two [N, N] 16-bit buffers; nothing is accumulated across launches.
+void etai_unet::self_attention_bwd_gemm(const TapeRec& r, const void* dy, char* dqkv, bool plan, cudaStream_t s) {
+    const int C = r.C, heads = r.heads, d = r.d, N = (int)r.HW;
+    const int DP = (d + 63) / 64 * 64;
+    const size_t hp = (size_t)heads * N * DP * esz;
+    char* qp = (char*)garena.alloc(hp);  char* qpT = (char*)garena.alloc(hp);
+    char* kp = (char*)garena.alloc(hp);  char* kpT = (char*)garena.alloc(hp);
+    char* vp = (char*)garena.alloc(hp);
+    char* dop = (char*)garena.alloc(hp); char* dopT = (char*)garena.alloc(hp);
+    char* dqp = (char*)garena.alloc(hp); char* dkp = (char*)garena.alloc(hp); char* dvp = (char*)garena.alloc(hp);
+    char* b1 = (char*)garena.alloc((size_t)N * N * esz);
+    char* b2 = (char*)garena.alloc((size_t)N * N * esz);
+    float* lse = (float*)garena.alloc((size_t)N * sizeof(float));
+    float* dsum = (float*)garena.alloc((size_t)heads * N * sizeof(float));
+    if (plan) return;
+    auto mm = [&](const void* A, long lda, const void* W, void* Cc, long M, int Nn, int K, long ldc) {
+        GemmArgs g;
+        g.A = A; g.W = W; g.C = Cc; g.M = M; g.N = Nn; g.K = K; g.lda = lda; g.ldc = ldc; g.ldr = ldc;
+        gemm(g, s);
+    };
+    for (int b = 0; b < r.B; ++b) {
+        const char* qkv = (const char*)r.x + (size_t)b * N * 3 * C * esz;
+        const char* o = (const char*)r.y + (size_t)b * N * C * esz;
+        const char* dO = (const char*)dy + (size_t)b * N * C * esz;
+        attn_pack_heads(qkv, 3 * C, N, heads, d, DP, qp, qpT, dt, s);
+        attn_pack_heads(qkv + (size_t)C * esz, 3 * C, N, heads, d, DP, kp, kpT, dt, s);
+        attn_pack_heads(qkv + (size_t)2 * C * esz, 3 * C, N, heads, d, DP, vp, nullptr, dt, s);
+        attn_pack_heads(dO, C, N, heads, d, DP, dop, dopT, dt, s);
+        attn_rowdot(dO, C, o, C, N, heads, d, dsum, dt, s);
+        launches += 5;
+        for (int h = 0; h < heads; ++h) {
+            const size_t ho = (size_t)h * N * DP * esz;  // same offset for [N,DP] and [DP,N] blocks
+            const float* D = dsum + (size_t)h * N;
+            mm(qp + ho, DP, kp + ho, b1, N, N, DP, N);                                   // S
+            softmax_rows(b1, N, N, r.scale, dt, s, lse);                                 // P, lse
+            mm(dop + ho, DP, vp + ho, b2, N, N, DP, N);                                  // dP
+            attn_bwd_elementwise(b2, b1, D, N, N, r.scale, 0, dt, s);                    // dS
+            mm(b2, N, kpT + ho, dqp + ho, N, DP, N, DP);                                 // dQ = dS K
+            mm(kp + ho, DP, qp + ho, b1, N, N, DP, N);                                   // S^T
+            attn_bwd_elementwise(b1, nullptr, lse, N, N, r.scale, 1, dt, s);             // P^T
+            mm(b1, N, dopT + ho, dvp + ho, N, DP, N, DP);                                // dV = P^T dO
+            mm(vp + ho, DP, dop + ho, b2, N, N, DP, N);                                  // dP^T
+            attn_bwd_elementwise(b2, b1, D, N, N, r.scale, 2, dt, s);                    // dS^T
+            mm(b2, N, qpT + ho, dkp + ho, N, DP, N, DP);                                 // dK = dS^T Q
+            launches += 4;
+        }
+        char* dst = dqkv + (size_t)b * N * 3 * C * esz;
+        attn_unpack_heads(dqp, N, heads, d, DP, dst, 3 * C, dt, s);
+        attn_unpack_heads(dkp, N, heads, d, DP, dst + (size_t)C * esz, 3 * C, dt, s);
+        attn_unpack_heads(dvp, N, heads, d, DP, dst + (size_t)2 * C * esz, 3 * C, dt, s);
+        launches += 3;
     }
 }
 

@@ -88,6 +88,8 @@ def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int, pipes: i
                                                     unet_state_dict=usd)
     all_pipes = [pipe] + [clone_pipeline(pipe) for _ in range(max(1, pipes) - 1)]  # groups in flight per GPU
     del usd
+    from concurrent.futures import ThreadPoolExecutor
+    writer, writes = ThreadPoolExecutor(max_workers=4, thread_name_prefix="etai-png"), []  # PNG encode + write off the drivers
     for ci, combo in combos(spec):
         data = combo["data"] if isinstance(combo["data"], dict) else {"type": combo["data"]}
         n = min(int(data.get("n", 700)), limit) if limit else int(data.get("n", 700))
@@ -135,7 +137,11 @@ def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int, pipes: i
                     if r is None:
                         recs[s["name"]] = {"name": s["name"], "status": "unsupported"}
                         continue
-                    cv2.imwrite(str(out_dir / f"{s['name']}.png"), cv2.cvtColor(postproc(r["image"]), cv2.COLOR_RGB2BGR))
+                    # device -> host uint8 here (orders after the group's stream); PNG encode + file write on the writer pool
+                    # (cv2 releases the GIL), so the pipe's driver thread goes straight on to its next group
+                    img = postproc(r["image"])
+                    writes.append(writer.submit(lambda path=str(out_dir / f"{s['name']}.png"), im=img:
+                                                cv2.imwrite(path, cv2.cvtColor(im, cv2.COLOR_RGB2BGR))))
                     lat = r["latent"][0] if isinstance(r["latent"], (list, tuple)) else r["latent"]  # EDICT: coupled pair
                     recs[s["name"]] = {"name": s["name"], "status": "done", "latent_mean": float(lat.mean())}
                 out.append([recs.get(s["name"], {"name": s["name"], "status": "skipped"}) for s in ss])
@@ -147,7 +153,13 @@ def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int, pipes: i
             dist.barrier()
         t_sweep = time.perf_counter()
         records = run_sweep(n, rank, world, cobatch, run_group, window=4 * len(all_pipes), run_groups=run_groups)
-        t_sweep = time.perf_counter() - t_sweep  # includes the final gather = the slowest rank
+        for w in writes:  # every PNG of this rank is on disk before the sweep counts as finished
+            if not w.result():
+                raise RuntimeError("cv2.imwrite failed")
+        writes.clear()
+        if world > 1:
+            dist.barrier()
+        t_sweep = time.perf_counter() - t_sweep  # includes the final gather and the PNG writes of the slowest rank
         if rank == 0:
             done = sum(r['status'] == 'done' for r in records)
             print(f"combo {ci}: {done} edits in {t_sweep:.1f} s on {world} GPU(s) = {done / max(t_sweep, 1e-9):.2f} edits/s "
