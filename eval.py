@@ -181,5 +181,5 @@ if __name__ == "__main__":
     ap.add_argument("--skip_existing_dirs", action="store_true", help="Skips existing directories.")
     ap.add_argument("--prec", default="fp16", choices=["fp16", "bf16", "fp32"])
     ap.add_argument("--limit", type=int, default=0, help="Only the first N samples (smoke runs).")
-    ap.add_argument("--pipes", type=int, default=2, help="Lock-step groups in flight per GPU (each on its own engine).")
+    ap.add_argument("--pipes", type=int, default=3, help="Lock-step groups in flight per GPU (each on its own engine handle).")
     main(**vars(ap.parse_args()))
