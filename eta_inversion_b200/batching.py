@@ -48,7 +48,7 @@ class LockstepGroup:
         self._gen = 0
         self._err: Optional[BaseException] = None
         self._aborted = False
-        self._ctx_key, self._ctx_cat = None, None
+        self._ctx_key, self._ctx_cat, self._ctx_role_major = None, None, False
         self._table_cache: Dict[str, Any] = {}
         self._store_cache = None
         self.forwards = 0
@@ -106,43 +106,54 @@ class LockstepGroup:
         for s, t, c, _ in reqs:
             if s.shape[0] != B or float(t) != t0 or c is None or c.shape[0] != B:
                 raise RuntimeError("lanes disagree on batch rows / timestep / context rows")
-        sample = torch.cat([r[0] for r in reqs])
+        L = len(reqs)
+        # Row layout of the merged batch.  Lane-major (lane l owns rows [l*B, (l+1)*B)) unless a lane asks for Plug-and-Play's
+        # feature injection: the engine copies rows [0, n) over rows [n, 3n) (pnp_utils.py:172-177), so the lanes' source
+        # rows must come first -- role-major, row r of lane l at r*L + l.
+        role_major = any(r[3] is not None and r[3].conv_inject_rows for r in reqs)
+        if role_major:
+            sample = torch.stack([r[0] for r in reqs], 1).flatten(0, 1)
+        else:
+            sample = torch.cat([r[0] for r in reqs])
         old = self._ctx_key  # strong references to the lanes' context tensors + their versions (addresses can be reused)
-        same = old is not None and len(old) == len(reqs) and all(o[0] is r[2] and o[1] == r[2]._version
-                                                                 for o, r in zip(old, reqs))
+        same = (old is not None and len(old) == L and self._ctx_role_major == role_major
+                and all(o[0] is r[2] and o[1] == r[2]._version for o, r in zip(old, reqs)))
         if not same:  # contexts are constant over a loop: concatenate (and re-project K/V) only on change
             self._ctx_key = [(r[2], r[2]._version) for r in reqs]
-            self._ctx_cat = torch.cat([r[2] for r in reqs]).contiguous()
-        ctrl, scatter = self._merge([r[3] for r in reqs], B)
+            self._ctx_role_major = role_major
+            self._ctx_cat = (torch.stack([r[2] for r in reqs], 1).flatten(0, 1) if role_major
+                             else torch.cat([r[2] for r in reqs])).contiguous()
+        ctrl, scatter = self._merge([r[3] for r in reqs], B, role_major)
         eps = self.engine(sample, t0, encoder_hidden_states=self._ctx_cat, control=ctrl)["sample"]
         for fn in scatter:
             fn()
         for i, l in enumerate(order):
-            self._out[l] = eps[i * B:(i + 1) * B]
+            self._out[l] = eps[i::L] if role_major else eps[i * B:(i + 1) * B]
         self.forwards += 1
 
-    def _merge(self, ctrls: Sequence[Optional[AttnControl]], B: int):
+    def _merge(self, ctrls: Sequence[Optional[AttnControl]], B: int, role_major: bool = False):
         if all(c is None for c in ctrls):
             return None, []
         out = AttnControl()
         scatter: List[Callable[[], None]] = []
+        L = len(ctrls)
+        rm = (lambda l, r: r * L + l) if role_major else (lambda l, r: l * B + r)  # merged row of row r of lane l
         # self-attention remap: lanes without one keep identity rows
         if any(c is not None and c.self_rows is not None for c in ctrls):
-            q, k, v = [], [], []
             masks = {(c.self_layer_mask, c.self_max_tokens) for c in ctrls if c is not None and c.self_rows is not None}
             if len(masks) != 1:
                 raise RuntimeError("lanes disagree on the self-attention remap window")
             out.self_layer_mask, out.self_max_tokens = masks.pop()
+            q, k, v = [0] * (L * B), [0] * (L * B), [0] * (L * B)
             for l, c in enumerate(ctrls):
                 rows = c.self_rows if (c is not None and c.self_rows is not None) else ([*range(B)],) * 3
-                q += [l * B + r for r in rows[0]]
-                k += [l * B + r for r in rows[1]]
-                v += [l * B + r for r in rows[2]]
+                for r in range(B):
+                    q[rm(l, r)], k[rm(l, r)], v[rm(l, r)] = rm(l, rows[0][r]), rm(l, rows[1][r]), rm(l, rows[2][r])
             out.self_rows = (q, k, v)
         # cross-attention edit: one (base, target) pair per lane that edits at this step
         ed = [(l, c) for l, c in enumerate(ctrls) if c is not None and c.edit_pairs is not None]
         if ed:
-            out.edit_pairs = [(l * B + b, l * B + t) for l, c in ed for (b, t) in c.edit_pairs]
+            out.edit_pairs = [(rm(l, b), rm(l, t)) for l, c in ed for (b, t) in c.edit_pairs]
             for name in ("mapper", "blend_a", "equalizer", "alpha_step"):
                 parts = [getattr(c, name) for _, c in ed]
                 # mapper / blend_a / equalizer are the same tensor objects for a whole loop: concatenate once, not per forward
@@ -160,7 +171,7 @@ class LockstepGroup:
             if len(res) != 1:
                 raise RuntimeError("lanes disagree on the attention-store resolution")
             out.store_res = res.pop()
-            out.store_rows = [l * B + r for l, c in st for r in c.store_rows]
+            out.store_rows = [rm(l, r) for l, c in st for r in c.store_rows]
             n = len(out.store_rows)
             places = [p for p in ("store_down", "store_mid", "store_up") if any(getattr(c, p) is not None for _, c in st)]
             # one combined accumulator per place, kept across forwards and re-zeroed with ONE multi-tensor launch; the lanes'
@@ -185,8 +196,12 @@ class LockstepGroup:
                     off += m
             if dsts:
                 scatter.append(lambda dsts=dsts, srcs=srcs: torch._foreach_add_(dsts, srcs))
-        if any(c is not None and c.conv_inject_rows for c in ctrls):
-            raise NotImplementedError("Plug-and-Play feature injection is not supported in lock-step groups")
+        if role_major:
+            # every lane injects its row 0 into its rows 1, 2: with the source rows first this is ONE block copy in the engine
+            if any(c is None or c.conv_inject_rows != 1 for c in ctrls) or B != 3:
+                raise RuntimeError("lanes disagree on the Plug-and-Play feature injection (every lane must inject 1 source row "
+                                   "into its 3-row batch at this step)")
+            out.conv_inject_rows = L
         return out, scatter
 
 

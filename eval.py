@@ -120,10 +120,10 @@ def main(cfg: str, cobatch: int, override: bool, prec: str, limit: int, pipes: i
                           cfg={**s["edit_cfg"]} if edit_method["type"] == "ptp" else None,
                           inv_cfg=dict(edit_word_idx=s["edit_word_idx"])) for s in td] for td in todo]
             live = [g for g, j in enumerate(jobs) if j]
-            # one edit at a time: PnP's feature injection is not mergeable across lanes, and null-text inversion differentiates
-            # the UNet (its per-step optimisation has a data-dependent length), so config 5 of BASELINE.json runs as
-            # independent replicas: one edit per GPU at a time, samples sharded over the ranks
-            if edit_method["type"] == "pnp" or method.get("type") == "nti":
+            # one edit at a time: null-text inversion differentiates the UNet (its per-step optimisation has a data-dependent
+            # length), so config 5 of BASELINE.json runs as independent replicas: one edit per GPU at a time, samples sharded
+            # over the ranks.  (Plug-and-Play edits are co-batched like the others: the merged batch is laid out role-major.)
+            if method.get("type") == "nti":
                 with torch.no_grad():
                     res = {g: [make_editor(pipe).edit(**j) for j in jobs[g]] for g in live}
             elif len(all_pipes) > 1 and len(live) > 1:

@@ -69,9 +69,9 @@ def test_merge_rejects_inconsistent_lanes():
     with pytest.raises(RuntimeError, match="attention-store resolution"):
         grp._merge([a, b], 4)
     b = _ptp_ctrl(2.0)
-    b.conv_inject_rows = 1
-    with pytest.raises(NotImplementedError):
-        grp._merge([a, b], 4)
+    b.conv_inject_rows = 1  # one lane injects Plug-and-Play features, the other does not (and the batch is not PnP's 3 rows)
+    with pytest.raises(RuntimeError, match="Plug-and-Play"):
+        grp._merge([a, b], 4, role_major=True)
 
 
 def test_lanes_rendezvous_into_one_forward_and_get_their_rows_back():
@@ -144,3 +144,37 @@ def test_a_lane_that_finishes_early_releases_its_peers():
     assert [c[0].shape[0] for c in eng.calls] == [4, 4, 2]
     assert res[0][:, 0, 0, 0].tolist() == [0.0, 3.0]            # rows 0,1 in every forward
     assert res[2][:, 0, 0, 0].tolist() == [2.0 + 2 * 2, 2.0 + 2 * 3]  # rows 2,3 of the two shared forwards
+
+
+def test_merge_role_major_for_plug_and_play():
+    """Plug-and-Play lanes (3 rows: source, uncond, cond; row 0's features and q/k are injected into rows 1, 2) are merged
+    role-major -- all sources first -- so that the engine's block copy rows [0, n) -> [n, 3n) serves every lane."""
+    eng = _StubEngine()
+    grp = LockstepGroup(eng, lanes=2)
+
+    def pnp_ctrl():
+        c = AttnControl(conv_inject_rows=1)
+        c.self_rows = ([0, 0, 0], [0, 0, 0], [0, 1, 2])
+        c.self_layer_mask = 0xFF00
+        return c
+    merged, _ = grp._merge([pnp_ctrl(), pnp_ctrl()], B=3, role_major=True)
+    assert merged.conv_inject_rows == 2
+    # merged row of (lane l, row r) = r * 2 + l: rows [src0, src1, unc0, unc1, cond0, cond1]
+    assert merged.self_rows[0] == [0, 1, 0, 1, 0, 1] and merged.self_rows[1] == [0, 1, 0, 1, 0, 1]
+    assert merged.self_rows[2] == [0, 1, 2, 3, 4, 5] and merged.self_layer_mask == 0xFF00
+    with pytest.raises(RuntimeError, match="Plug-and-Play"):
+        grp._merge([pnp_ctrl(), AttnControl()], B=3, role_major=True)
+    # the rendez-vous lays samples / contexts out the same way and hands every lane its own rows back
+    outs = [None, None]
+
+    def lane(l):
+        x = torch.full((3, 4, 8, 8), float(10 * l)) + torch.arange(3, dtype=torch.float32).reshape(3, 1, 1, 1)
+        outs[l] = grp.forward(l, x, 500, torch.full((3, 77, 768), float(l)), pnp_ctrl())["sample"]
+    ths = [threading.Thread(target=lane, args=(l,)) for l in range(2)]
+    [t.start() for t in ths]
+    [t.join() for t in ths]
+    sample, _, ctx, ctrl = eng.calls[-1]
+    assert sample[:, 0, 0, 0].tolist() == [0.0, 10.0, 1.0, 11.0, 2.0, 12.0] and ctx[:, 0, 0].tolist() == [0, 1, 0, 1, 0, 1]
+    assert ctrl.conv_inject_rows == 2
+    # stub: eps = sample + merged row index -> lane 0 rows 0, 2, 4 ; lane 1 rows 1, 3, 5
+    assert outs[0][:, 0, 0, 0].tolist() == [0.0, 3.0, 6.0] and outs[1][:, 0, 0, 0].tolist() == [11.0, 14.0, 17.0]
