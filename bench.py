@@ -367,6 +367,9 @@ def main():
                    "tflop_per_edit": round(2.0 * macs["total"] * rows / 1e12, 2),
                    "ms_per_unet_forward_avg": round(unet_graph_ms / (2 * args.inv_steps), 3),
                    "unet_share_of_step": round(unet_graph_ms / step_wall_ms, 3),
+                   "unet_share_note": "UNet-forward share of the wall time of ONE lock-step group running ALONE (nothing overlaps its "
+                                      "host work; depends on the box's host speed); in the timed regions the groups in flight hide "
+                                      "that time: see clocks.gpu_util_pct_mean",
                    "parallelism": f"per-image sharding, {world} independent rank(s), no collective in the loop"},
         "clocks": clocks.summary(),
         "e2e": {"value": world * K * CB * G / e2e_s, "unit": "edits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -125,13 +125,19 @@ def load() -> C.CDLL:
     return lib
 
 
-def tensor_table(state_dict):
-    """state_dict -> (ctypes array of etai_tensor, keep-alive list): the weight table every *_create entry point takes."""
+def tensor_table(state_dict, storage_dtype=None):
+    """state_dict -> (ctypes array of etai_tensor, keep-alive list): the weight table every *_create entry point takes.
+    ``storage_dtype``: plain tensors (vectors, matrices, 1x1 convolutions) are converted to the engine's storage dtype here, on
+    the host (same round-to-nearest as the device kernel), so the library only copies them; 3x3 filters and the GEGLU
+    projection are re-packed on the device from fp32 and stay as they are."""
     keep, arr = [], (EtaiTensor * len(state_dict))()
     for i, (name, t) in enumerate(state_dict.items()):
         t = t.detach()
         if t.dtype not in (torch.float32, torch.float16, torch.bfloat16):
             t = t.float()
+        plain = t.ndim <= 2 or tuple(t.shape[2:]) == (1, 1)
+        if storage_dtype is not None and plain and ".ff.net.0.proj." not in name and t.dtype != storage_dtype:
+            t = t.to(storage_dtype)
         t = t.contiguous()
         keep.append(t)
         arr[i].name = name.encode()

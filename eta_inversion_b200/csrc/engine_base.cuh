@@ -143,8 +143,19 @@ struct OpCtx {
     }
     // plain tensor converted to storage dtype at dst (device)
     void put(const std::string& name, std::initializer_list<int64_t> shape, void* dst) {
+        const etai_tensor& t = find(name);
+        if (t.dtype == dt) {  // already in the storage dtype (the Python loader converts plain tensors on the host): one copy, no kernel
+            ETAI_CHECK(t.ndim == (int)shape.size(), ETAI_ERR_ARG, ("bad rank for " + name).c_str());
+            int i = 0;
+            for (int64_t d : shape) {
+                ETAI_CHECK(t.shape[i] == d, ETAI_ERR_ARG, ("bad shape for " + name).c_str());
+                ++i;
+            }
+            CUDA_CHECK(cudaMemcpy(dst, t.data, numel(t) * esz, t.on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+            return;
+        }
         const float* s = staged(name, shape);
-        size_t n = numel(find(name));
+        size_t n = numel(t);
         convert(s, ETAI_F32, dst, dt, (long)n, 0);
         CUDA_CHECK(cudaStreamSynchronize(0));
     }

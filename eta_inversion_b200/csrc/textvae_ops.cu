@@ -90,8 +90,8 @@ __global__ void quick_gelu_k(T* __restrict__ x, long nvec) {
     store8<T>(x + i * 8, a);
 }
 
-// qkv: [B*L, 3C] (q | k | v), head h at column h*D; out: [B*L, C].  grid (heads, B), 256 threads = 8 warps, warp w takes
-// query rows w, w+8, ...; lane j owns keys j, j+32, j+64 for the scores and output columns j, j+32 for PV.
+// qkv: [B*L, 3C] (q | k | v), head h at column h*D; out: [B*L, C].  grid (heads, B, query chunks), 256 threads = 8 warps, warp w
+// takes query rows w, w+8, ... of its chunk; lane j owns keys j, j+32, j+64 for the scores and output columns j, j+32 for PV.
 template <typename T, int D>
 __global__ void __launch_bounds__(256) clip_attention_k(const T* __restrict__ qkv, T* __restrict__ out, int L, int C, float scale) {
     extern __shared__ float smf[];
@@ -107,7 +107,8 @@ __global__ void __launch_bounds__(256) clip_attention_k(const T* __restrict__ qk
     }
     __syncthreads();
     float* P = Ps + warp * 96;
-    for (int i = warp; i < L; i += 8) {
+    const int qc = (L + gridDim.z - 1) / gridDim.z, q_lo = blockIdx.z * qc, q_hi = q_lo + qc < L ? q_lo + qc : L;
+    for (int i = q_lo + warp; i < q_hi; i += 8) {
         float q[D / 32];  // this lane's slice of the query is not enough for a dot product: broadcast through shuffles
 #pragma unroll
         for (int t = 0; t < D / 32; ++t) q[t] = to_f<T>(base[(long)i * 3 * C + t * 32 + lane]) * scale;
@@ -183,7 +184,7 @@ void clip_attention(const void* qkv, void* out, int B, int L, int heads, int d, 
     ETAI_DISPATCH_DTYPE(dtype, T, {
         auto k = clip_attention_k<T, 64>;
         CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        k<<<dim3(heads, B), 256, smem, s>>>((const T*)qkv, (T*)out, L, C, scale);
+        k<<<dim3(heads, B, 5), 256, smem, s>>>((const T*)qkv, (T*)out, L, C, scale);  // 5 chunks of <= 16 queries: 2 per warp
     });
     KERNEL_CHECK();
 }

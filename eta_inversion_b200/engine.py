@@ -155,20 +155,7 @@ class UNetEngine:
         for i, c in enumerate(channels):
             cfg.block_out_channels[i] = c
         cfg.heads, cfg.cross_dim, cfg.ctx_len, cfg.latent_hw, cfg.max_batch = heads, cross_dim, ctx_len, latent_hw, max_batch
-        keep, arr = [], (EtaiTensor * len(state_dict))()
-        for i, (name, t) in enumerate(state_dict.items()):
-            t = t.detach()
-            if t.dtype not in (torch.float32, torch.float16, torch.bfloat16):
-                t = t.float()
-            t = t.contiguous()
-            keep.append(t)
-            arr[i].name = name.encode()
-            arr[i].data = t.data_ptr()
-            arr[i].dtype = dtype_code(t.dtype)
-            arr[i].ndim = t.ndim
-            for d in range(t.ndim):
-                arr[i].shape[d] = t.shape[d]
-            arr[i].on_device = 1 if t.is_cuda else 0
+        arr, keep = _lib.tensor_table(state_dict, dtype)  # plain tensors converted to the storage dtype on the host
         h = C.c_void_p()
         with torch.cuda.device(dev):
             check(lib.etai_unet_create(C.byref(h), C.byref(cfg), arr, len(state_dict), dev.index or 0))

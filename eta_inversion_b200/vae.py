@@ -39,7 +39,7 @@ class VAEEngine:
         cfg.dtype, cfg.math_mode, cfg.image_hw, cfg.max_batch = dtype_code(dtype), math_mode, image_hw, max_batch
         for i, c in enumerate(channels):
             cfg.block_out_channels[i] = c
-        arr, keep = tensor_table(state_dict)
+        arr, keep = tensor_table(state_dict, dtype)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             check(lib.etai_vae_create(C.byref(h), C.byref(cfg), arr, len(state_dict), self.device.index or 0))
@@ -109,7 +109,7 @@ class CLIPTextEngine:
         cfg.vocab, cfg.hidden, cfg.layers, cfg.heads, cfg.ffn, cfg.max_len, cfg.max_batch = (vocab, hidden, layers, heads, ffn,
                                                                                             max_len, max_batch)
         sd = {k: v for k, v in state_dict.items() if not k.endswith("position_ids")}
-        arr, keep = tensor_table(sd)
+        arr, keep = tensor_table(sd, dtype)
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             check(lib.etai_clip_create(C.byref(h), C.byref(cfg), arr, len(sd), self.device.index or 0))
