@@ -288,7 +288,7 @@ def main():
         n = 0
         for res in results:
             out = [postproc(res["image"]), postproc(res["image_inv"])]  # device -> host uint8 images (cv2.imwrite input)
-            n += res["image"].numel() * res["image"].element_size() * 2
+            n += sum(o.nbytes for o in out)  # the bytes that actually cross PCIe: HWC uint8 (converted on the device)
         d2h_box[0] = n * G  # per step
         return None
 
