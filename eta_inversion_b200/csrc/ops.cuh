@@ -124,8 +124,9 @@ void scale_by_device_scalar(const void* in, void* out, const float* s_dev, bool 
 void absmax_scale(const float* x, long n, float target, float* s_dev, cudaStream_t s);
 void geglu_fwd(const void* u, void* y, long M, int F, int dtype, cudaStream_t s);
 void geglu_bwd(const void* u, const void* dy, void* du, long M, int F, int dtype, cudaStream_t s);
+size_t groupnorm_bwd_workspace_bytes(int B, int groups);
 void groupnorm_bwd(const void* x, const void* dy, const void* gamma, const void* beta, void* dx, int B, long HW, int C,
-                   int groups, float eps, bool silu, int dtype, cudaStream_t s);
+                   int groups, float eps, bool silu, int dtype, void* ws, cudaStream_t s);
 void layernorm_bwd(const void* x, const void* dy, const void* gamma, void* dx, long M, int C, float eps, int dtype,
                    cudaStream_t s);
 struct SelfAttnBwdArgs {
@@ -149,7 +150,7 @@ struct CrossAttnBwdArgs {
     float scale;
     int dtype;
 };
-// ---- pieces of the GEMM-based self-attention backward (16-bit engines, N >= 1024): every N x N product runs on gemm_tc_k
+// ---- pieces of the GEMM-based self-attention backward (16-bit engines, N >= 256): every N x N product runs on gemm_tc_k
 // head slices [N, d] (row stride ld) -> zero-padded [heads][N][DP] and its transpose [heads][DP][N] (dstT may be null)
 void attn_pack_heads(const void* src, long ld, int N, int heads, int d, int DP, void* dst, void* dstT, int dtype, cudaStream_t s);
 void attn_unpack_heads(const void* src, int N, int heads, int d, int DP, void* dst, long ld, int dtype, cudaStream_t s);

@@ -722,7 +722,8 @@ void etai_unet::backward_walk(int B, cudaStream_t s) {
         case T_GN: {
             const long n = (long)r.B * r.HW * r.n.c;
             void* dx = garena.alloc((size_t)n * esz);
-            if (!plan) { groupnorm_bwd(r.x, dy, r.n.g, r.n.b, dx, r.B, r.HW, r.n.c, 32, r.eps, r.silu, dt, s); launches += 1; }
+            void* gws = garena.alloc(groupnorm_bwd_workspace_bytes(r.B, 32));
+            if (!plan) { groupnorm_bwd(r.x, dy, r.n.g, r.n.b, dx, r.B, r.HW, r.n.c, 32, r.eps, r.silu, dt, gws, s); launches += 3; }
             add_grad(r.x, dx, n);
             break;
         }
@@ -738,7 +739,7 @@ void etai_unet::backward_walk(int B, cudaStream_t s) {
             const long M = (long)r.B * r.HW;
             char* dqkv = (char*)garena.alloc((size_t)M * 3 * C * esz);
             static const bool simt_only = [] { const char* e = getenv("ETAI_ATTN_BWD_SIMT"); return e && e[0] == '1'; }();
-            if (tc && r.HW >= 1024 && !simt_only) {
+            if (tc && r.HW >= 256 && !simt_only) {
                 const size_t mark = garena.off;
                 self_attention_bwd_gemm(r, dy, dqkv, plan, s);
                 garena.off = mark;  // the per-layer scratch is dead once the layer's kernels are enqueued (stream order)
@@ -822,7 +823,7 @@ void etai_unet::backward_walk(int B, cudaStream_t s) {
 }
 
 
-// Self-attention backward of one layer with every N x N product on the tensor-core GEMM kernel (16-bit engines, N >= 1024;
+// Self-attention backward of one layer with every N x N product on the tensor-core GEMM kernel (16-bit engines, N >= 256;
 // the SIMT flash-style kernels of backward.cu stay the fp32 parity path and serve the short sequences).  Per head, with
 // Qp / Kp / Vp / dOp the head's [N, DP] zero-padded slices and XpT their transposes:
 //   P    = softmax(scale Qp Kp^T) (+ lse)     dP   = dOp Vp^T       dS   = P   o (dP   - D[row]) scale      dQ = dS   Kp
