@@ -212,3 +212,22 @@ def test_null_text_loss_gradient_closed_form():
         coef = (1.0 - gs) * ((1.0 - a_p) ** 0.5 - (a_p ** 0.5) * ((1.0 - a_t) ** 0.5) / (a_t ** 0.5))
         closed = (rec.detach() - target) * (2.0 * coef / rec.numel())
         assert torch.allclose(e_u.grad, closed, rtol=2e-4, atol=1e-12), float((e_u.grad - closed).abs().max())
+
+
+def test_tensor_table_converts_plain_tensors_on_the_host():
+    """Weight table handed to etai_*_create: vectors, matrices and 1x1 convolutions are converted to the storage dtype on
+    the host (the library then only copies them); 3x3 filters and the GEGLU projection stay fp32 (re-packed on the device)."""
+    from eta_inversion_b200 import _lib
+    sd = {"a.norm.weight": torch.ones(8), "a.to_q.weight": torch.randn(8, 8), "a.proj_in.weight": torch.randn(8, 8, 1, 1),
+          "a.conv1.weight": torch.randn(8, 8, 3, 3), "b.ff.net.0.proj.weight": torch.randn(64, 8), "b.ff.net.0.proj.bias": torch.randn(64),
+          "ids": torch.arange(4)}
+    arr, keep = _lib.tensor_table(sd, torch.float16)
+    got = {arr[i].name.decode(): (arr[i].dtype, keep[i]) for i in range(len(sd))}
+    for name in ("a.norm.weight", "a.to_q.weight", "a.proj_in.weight"):
+        assert got[name][0] == _lib.ETAI_F16 and got[name][1].dtype == torch.float16
+        assert torch.equal(got[name][1], sd[name].to(torch.float16))
+    for name in ("a.conv1.weight", "b.ff.net.0.proj.weight", "b.ff.net.0.proj.bias"):
+        assert got[name][0] == _lib.ETAI_F32 and got[name][1].dtype == torch.float32
+    assert got["ids"][1].dtype == torch.float16            # integer tensors are widened to float first, then plain
+    arr32, keep32 = _lib.tensor_table(sd)                    # no storage dtype: nothing is converted
+    assert all(k.dtype == torch.float32 for k in keep32)
