@@ -139,6 +139,12 @@ class DiffusionInversion:
         return self.model.text_encoder(tok.input_ids)[0].float()  # ids are host data; the native tower uploads them
 
     def create_context(self, prompt: str, negative_prompt: str = "") -> torch.Tensor:
+        if negative_prompt is not None and not getattr(self.model, "cache_text_embeddings", True):
+            # no memo (bench.py): both prompts in ONE pass of the text tower instead of two (rows are independent: same
+            # numbers as two B = 1 passes, half the launches)
+            tok = self.model.tokenizer([negative_prompt, prompt], padding="max_length",
+                                       max_length=self.model.tokenizer.model_max_length, truncation=True, return_tensors="pt")
+            return self.model.text_encoder(tok.input_ids)[0].float().contiguous()
         text_embeddings = self._embed(prompt)
         if negative_prompt is not None:
             return torch.cat([self._embed(negative_prompt), text_embeddings]).contiguous()
