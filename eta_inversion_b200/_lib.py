@@ -88,6 +88,7 @@ SYMBOLS = {
     "etai_clip_launch_count": (_i64, [_vp]),
     "etai_cfg_ddim_step": (C.c_int, [_vp, _i32, _i32, _f, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _i32, _vp, _i64, _vp]),
     "etai_eta_noise_losses": (C.c_int, [_vp, _i32, _i32, _f, _vp, _vp, _f, _f, _f, _f, _vp, _i32, _i64, _vp, _vp, _vp]),
+    "etai_prox_guidance": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _f, _f, _i32, _f, _vp, _vp]),
     "etai_groupnorm": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _f, _i32, _i32, _vp, _i64, _vp]),
     "etai_layernorm": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i32, _f, _i32, _vp]),
     "etai_gemm": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),

@@ -54,6 +54,16 @@ int etai_eta_noise_losses(const float* eps, int32_t n, int32_t has_cfg, float gu
     ETAI_API_END
 }
 
+int etai_prox_guidance(const float* eps_u, const float* eps_c, float* out, int64_t n, int64_t rank_lo, int64_t rank_hi,
+                       float weight, float fixed_thr, int32_t l1, float guidance, float* thr_out, void* stream) {
+    ETAI_API_BEGIN
+    ETAI_CHECK(eps_u && eps_c && out && n >= 1, ETAI_ERR_ARG, "prox_guidance: null/empty argument");
+    ETAI_CHECK(rank_lo < 0 || (rank_lo < n && rank_hi >= rank_lo && rank_hi <= rank_lo + 1 && rank_hi < n), ETAI_ERR_ARG,
+               "prox_guidance: need 0 <= rank_lo <= rank_hi <= rank_lo + 1 < n (or rank_lo < 0 for a fixed threshold)");
+    prox_guidance(eps_u, eps_c, out, n, rank_lo, rank_hi, weight, fixed_thr, l1, guidance, thr_out, (cudaStream_t)stream);
+    ETAI_API_END
+}
+
 int etai_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int32_t B, int64_t HW, int32_t C,
                    int32_t groups, float eps, int32_t silu, int32_t dtype, void* workspace, int64_t workspace_bytes,
                    void* stream) {

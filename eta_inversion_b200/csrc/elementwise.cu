@@ -1,4 +1,4 @@
-// Data-movement, weight-repack and fused scheduler kernels (HBM / latency bound; vectorised, no atomics).
+// Data-movement, weight-repack and fused scheduler kernels (HBM / latency bound; vectorised; no floating-point atomics).
 #include "ops.cuh"
 
 namespace etai {
@@ -374,6 +374,113 @@ void eta_noise_losses(const float* eps, int n, int has_cfg, float guidance, cons
         argmin_k<<<1, 1, 0, s>>>(losses, K, best_idx);
         KERNEL_CHECK();
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Proximal CFG of proximal negative-prompt inversion (proximal_negative_prompt_inversion.py:61-128): the threshold is a
+// global quantile of |eps_c - eps_u| (2 x 16384 values), which the reference takes with torch.quantile (a full sort).
+// One CTA: non-negative floats order like their bit patterns, so four 8-bit radix-select passes over the keys (per-warp
+// integer histograms in shared memory -- integer counts, so the result does not depend on the order of the atomics)
+// find order statistic rank_lo, one more pass finds its successor, torch's 'linear' interpolation gives the threshold and
+// the last pass applies the soft threshold and the guidance.  Latency bound (the operands are 128 KB and stay in L1/L2).
+// ---------------------------------------------------------------------------------------------
+constexpr int PROX_THREADS = 1024, PROX_WARPS = PROX_THREADS / 32;
+
+__global__ void __launch_bounds__(PROX_THREADS) prox_guidance_k(const float* __restrict__ u, const float* __restrict__ c,
+                                                                float* __restrict__ out, long n, long rank_lo, long rank_hi,
+                                                                float weight, float fixed_thr, int l1, float g,
+                                                                float* __restrict__ thr_out) {
+    __shared__ unsigned hist[PROX_WARPS][256];
+    __shared__ unsigned total[256];
+    __shared__ unsigned s_prefix, s_equal, s_next, s_nan;
+    __shared__ long s_k, s_below;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float thr = fixed_thr;
+    if (rank_lo >= 0) {
+        if (tid == 0) { s_prefix = 0u; s_k = rank_lo; s_below = 0; s_next = 0xffffffffu; s_nan = 0u; s_equal = 0u; }
+        unsigned mask = 0u;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (int i = tid; i < PROX_WARPS * 256; i += PROX_THREADS) (&hist[0][0])[i] = 0u;
+            __syncthreads();
+            const unsigned prefix = s_prefix;
+            for (long e = tid; e < n; e += PROX_THREADS) {
+                const float d = fabsf(c[e] - u[e]);
+                if (d != d) s_nan = 1u;  // torch.quantile returns NaN when any element is NaN
+                const unsigned key = __float_as_uint(d);
+                if ((key & mask) == prefix) atomicAdd(&hist[warp][(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid < 256) {
+                unsigned t = 0;
+#pragma unroll 8
+                for (int w = 0; w < PROX_WARPS; ++w) t += hist[w][tid];
+                total[tid] = t;
+            }
+            __syncthreads();
+            if (warp == 0) {  // lane l owns bins [8l, 8l+8): locate the bin that holds rank s_k
+                unsigned loc[8], sum = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { loc[j] = total[lane * 8 + j]; sum += loc[j]; }
+                unsigned incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    unsigned v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const long k = s_k;
+                long before = (long)(incl - sum);
+                const bool mine = k >= before && k < (long)incl;  // exactly one lane (0 <= k < matching count)
+                __syncwarp();
+                if (mine) {
+                    int b = 0;
+                    while (k >= before + (long)loc[b]) { before += loc[b]; ++b; }
+                    s_prefix = prefix | ((unsigned)(lane * 8 + b) << shift);
+                    s_below += before;
+                    s_k = k - before;
+                    s_equal = loc[b];
+                }
+            }
+            mask |= 255u << shift;
+            __syncthreads();
+        }
+        const unsigned key_lo = s_prefix;
+        unsigned key_hi = key_lo;
+        if (rank_hi > rank_lo && s_below + (long)s_equal <= rank_hi) {  // successor = smallest key above key_lo
+            unsigned best = 0xffffffffu;
+            for (long e = tid; e < n; e += PROX_THREADS) {
+                const unsigned key = __float_as_uint(fabsf(c[e] - u[e]));
+                if (key > key_lo && key < best) best = key;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if (lane == 0) atomicMin(&s_next, best);
+            __syncthreads();
+            key_hi = s_next;
+        }
+        const float a = __uint_as_float(key_lo), b = __uint_as_float(key_hi), diff = b - a;
+        // at::native::lerp as nvcc contracts it: |w| < 0.5 ? a + w * (b - a) : b - (b - a) * (1 - w)
+        thr = weight < 0.5f ? __fmaf_rn(weight, diff, a) : __fmaf_rn(-diff, 1.0f - weight, b);
+        if (s_nan) thr = __uint_as_float(0x7fc00000u);
+    }
+    if (tid == 0 && thr_out) *thr_out = thr;
+    const bool bad = thr != thr;
+    for (long e = tid; e < n; e += PROX_THREADS) {
+        const float uu = u[e];
+        float d = c[e] - uu;
+        d = d - fminf(fmaxf(d, -thr), thr);
+        if (l1) {  // the reference's two torch.where lines, in order
+            d = d > 0.f ? d - thr : d;
+            d = d < 0.f ? d + thr : d;
+        }
+        const float r = __fadd_rn(uu, __fmul_rn(g, d));  // two roundings, like the reference's separate mul and add
+        out[e] = bad ? thr : r;
+    }
+}
+
+void prox_guidance(const float* eps_u, const float* eps_c, float* out, long n, long rank_lo, long rank_hi, float weight,
+                   float fixed_thr, int l1, float guidance, float* thr_out, cudaStream_t s) {
+    prox_guidance_k<<<1, PROX_THREADS, 0, s>>>(eps_u, eps_c, out, n, rank_lo, rank_hi, weight, fixed_thr, l1, guidance, thr_out);
+    KERNEL_CHECK();
 }
 
 }  // namespace etai

@@ -130,21 +130,32 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
-template <int BN>
+// SCHED 0: interleaved schedule, every k-block stage holds an A and a B box.
+// SCHED 1 ("B-stationary", K <= 320 projections): the CTA keeps its 160 x K slice of the weights resident in shared memory
+//          (BRES_KB k-blocks, loaded once) and walks a run of M tiles; the ring carries A boxes only, so the SM's TMA unit
+//          moves 128 instead of 288 operand rows per k-block.
+// EB = number of epilogue staging buffers (2: the conversion of tile i+1 does not wait for the TMA store of tile i to have
+//          read the panels; costs one ring stage).
+template <int BN, int SCHED = 0, int EB = 1>
 struct Smem {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGE_BYTES = SCHED == 1 ? A_BYTES : A_BYTES + B_BYTES;
+    static constexpr int BRES_KB = 5;                                      // K <= 320
+    static constexpr int BRES_BYTES = SCHED == 1 ? BRES_KB * B_BYTES : 0;
     // Epilogue staging: one pass of PW accumulator columns of all 128 rows, as column panels of 64 16-bit columns
     // ([128 rows][128 B], 128B-swizzled, so the row-per-lane writes are conflict free) plus a narrow tail panel; it leaves
     // through ONE TMA store per panel.  (Round 1 used a [32 x 32] box per warp and chunk: 20 store instructions per
-    // 128 x 160 tile cost the SM's TMA unit as much time as the tile's operand loads -- ETAI_GEMM_TRACE, r02_gemm_trace.)
+    // 128 x 160 tile cost the SM's TMA unit as much time as the tile's operand loads -- measured with ETAI_GEMM_TRACE.)
     static constexpr int PW = BN == 320 ? 160 : BN;            // accumulator columns per pass (a 320-wide tile takes two)
     static constexpr int PASSES = BN / PW;
     static constexpr int EPI_BYTES = (PW / 64) * 16384 + (PW % 64 ? 8192 : 0);
-    static constexpr int STAGES = (227 * 1024 - EPI_BYTES - 2048) / STAGE_BYTES > 6 ? 6 : (227 * 1024 - EPI_BYTES - 2048) / STAGE_BYTES;
-    static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BAR_OFF = EPI_OFF + EPI_BYTES;
+    static constexpr int EPI_BUFS = EB;
+    static constexpr int FREE = 227 * 1024 - EB * EPI_BYTES - BRES_BYTES - 2048;
+    static constexpr int STAGES = FREE / STAGE_BYTES > 6 ? 6 : FREE / STAGE_BYTES;
+    static constexpr int BRES_OFF = STAGES * STAGE_BYTES;
+    static constexpr int EPI_OFF = BRES_OFF + BRES_BYTES;
+    static constexpr int BAR_OFF = EPI_OFF + EB * EPI_BYTES;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;  // barriers + slack for manual 1024-B alignment
     // BN = 320 is issued as two UMMAs of N = 160 per k-step into two accumulators that sit side by side in TMEM (columns
     // [0,160) and [160,320)), so the epilogue sees one 320-column tile.  It is single-buffered (2 x 320 > 512 columns).
@@ -153,28 +164,62 @@ struct Smem {
     static constexpr int NBUF = BN == 320 ? 1 : 2;             // accumulator buffers in TMEM
     static constexpr int ACC_STRIDE = BN <= 128 ? 128 : 256;   // TMEM columns between the accumulator buffers (NBUF = 2)
     static constexpr int TMEM_COLS = BN == 320 ? 512 : 2 * ACC_STRIDE;
+    static_assert(STAGES >= 2, "smem ring too short");
+    static_assert(EB == 1 || PASSES == 1, "two staging buffers alternate per tile");
+    static_assert(SCHED == 0 || NACC == 1, "B-stationary schedule: one UMMA per k-step");
+    static_assert((2 * STAGES + 4 + BRES_KB) * 8 + 4 <= 256, "barrier area");
 };
 
-// Persistent kernel: grid = min(#work items, #SMs); every role walks the same static schedule
-//   item = blockIdx.x + i * gridDim.x ;  (split, m_tile, n_tile) = decode(item)
+// Static schedule of one CTA.  SCHED 0: item = blockIdx.x + li * gridDim.x over (split, m_tile, n_tile) with n fastest, so
+// the CTAs running at the same time share A panels in L2.  SCHED 1: gridDim.x = groups * tiles_n; CTA c owns N slice
+// c % tiles_n for its whole life and walks the M tiles of group c / tiles_n (the tiles_n CTAs of a group walk the same
+// A panels at the same time).
+template <int SCHED>
+struct Walk {
+    int count, n_fixed, m_begin;
+    __device__ __forceinline__ explicit Walk(const TcParams& p) {
+        if (SCHED == 1) {
+            const int ngroups = gridDim.x / p.tiles_n, g = blockIdx.x / p.tiles_n;
+            n_fixed = blockIdx.x % p.tiles_n;
+            m_begin = (int)((long)g * p.tiles_m / ngroups);
+            count = (int)((long)(g + 1) * p.tiles_m / ngroups) - m_begin;
+        } else {
+            const int items = p.tiles_m * p.tiles_n * p.splits;
+            n_fixed = m_begin = 0;
+            count = (int)blockIdx.x < items ? (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+        }
+    }
+    __device__ __forceinline__ void at(const TcParams& p, int li, int& split, int& m_tile, int& n_tile) const {
+        if (SCHED == 1) {
+            split = 0; m_tile = m_begin + li; n_tile = n_fixed;
+        } else {
+            const int item = blockIdx.x + li * gridDim.x, tiles = p.tiles_m * p.tiles_n, tile = item % tiles;
+            split = item / tiles; n_tile = tile % p.tiles_n; m_tile = tile / p.tiles_n;
+        }
+    }
+};
+
+// Persistent kernel: grid = min(#work items, #SMs); every role walks the same static schedule (Walk<SCHED>).
 // The smem ring runs across items, the accumulator is double buffered in TMEM so the epilogue of item i overlaps
 // the main loop of item i+1.
-template <typename T, int BN, bool CONV>
+template <typename T, int BN, bool CONV, int SCHED = 0, int EB = 1>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
           const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2,
           const __grid_constant__ TcParams p) {
-    using S = Smem<BN>;
+    using S = Smem<BN, SCHED, EB>;
+    static_assert(!(CONV && SCHED == 1), "the B-stationary schedule serves dense K <= 320 problems");
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint64_t* empty = full + S::STAGES;
     uint64_t* acc_full = empty + S::STAGES;   // [2]
     uint64_t* acc_empty = acc_full + 2;       // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+    uint64_t* b_full = acc_empty + 2;         // [BRES_KB] (SCHED 1: resident weight slice, filled once)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + S::BRES_KB);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int items = p.tiles_m * p.tiles_n * p.splits;
+    const Walk<SCHED> walk(p);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
@@ -183,6 +228,8 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         prefetch_tmap(&tmC2);
         for (int s = 0; s < S::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < S::NBUF; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS); }
+        if (SCHED == 1)
+            for (int k = 0; k < S::BRES_KB; ++k) mbar_init(&b_full[k], 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, S::TMEM_COLS);
@@ -195,10 +242,11 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (lane == 0) {
             // ===== TMA producer =====
             int kc = 0;  // k blocks issued so far by this CTA (ring position)
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int tile = item % (p.tiles_m * p.tiles_n), split = item / (p.tiles_m * p.tiles_n);
-                const int n0 = (tile % p.tiles_n) * BN;
-                const long m0 = (long)(tile / p.tiles_n) * BM;
+            for (int tli = 0; tli < walk.count; ++tli) {
+                int split, m_tile, n_tile;
+                walk.at(p, tli, split, m_tile, n_tile);
+                const int n0 = n_tile * BN;
+                const long m0 = (long)m_tile * BM;
                 int b0 = 0, oy0 = 0, ox0 = 0;
                 if (CONV) {
                     long hw = (long)p.Himg * p.Wimg;
@@ -208,9 +256,12 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = kb0 + p.kb_per_split < p.num_kb ? kb0 + p.kb_per_split : p.num_kb;
-                const int tli = (item - blockIdx.x) / gridDim.x;
                 if (p.trace && tli < TRACE_TILES) p.trace[((long)blockIdx.x * TRACE_TILES + tli) * TRACE_SLOTS + 0] = clock64();
                 for (int kb = kb0; kb < kb1; ++kb, ++kc) {
+                    if (SCHED == 1 && tli == 0) {  // the weight slice of this CTA, k-block by k-block ahead of the first tile's A boxes
+                        mbar_expect_tx(&b_full[kb], S::B_BYTES);
+                        tma_load_2d(smem + S::BRES_OFF + kb * S::B_BYTES, &tmB, &b_full[kb], kb * BK, n0);
+                    }
                     int s = kc % S::STAGES;
                     uint32_t ph = (kc / S::STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
@@ -223,9 +274,11 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     } else {
                         tma_load_2d(sa, &tmA, &full[s], kb * BK, (int)m0);
                     }
+                    if (SCHED == 0) {
 #pragma unroll
-                    for (int j = 0; j < S::NACC; ++j)  // a TMA box has at most 256 rows: one box per UMMA-N slice of the tile
-                        tma_load_2d(sb + j * S::UN * 128, &tmB, &full[s], kb * BK, n0 + j * S::UN);
+                        for (int j = 0; j < S::NACC; ++j)  // a TMA box has at most 256 rows: one box per UMMA-N slice of the tile
+                            tma_load_2d(sb + j * S::UN * 128, &tmB, &full[s], kb * BK, n0 + j * S::UN);
+                    }
                 }
                 if (p.trace && tli < TRACE_TILES) p.trace[((long)blockIdx.x * TRACE_TILES + tli) * TRACE_SLOTS + 1] = clock64();
             }
@@ -234,9 +287,10 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (lane == 0) {
             // ===== MMA issuer =====
             const uint32_t idesc = make_idesc_f16(p.fmt, BM, S::UN);
-            int kc = 0, li = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
-                const int split = item / (p.tiles_m * p.tiles_n);
+            int kc = 0;
+            for (int li = 0; li < walk.count; ++li) {
+                int split, m_tile, n_tile;
+                walk.at(p, li, split, m_tile, n_tile);
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = kb0 + p.kb_per_split < p.num_kb ? kb0 + p.kb_per_split : p.num_kb;
                 const int buf = li % S::NBUF;
@@ -250,11 +304,12 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     int s = kc % S::STAGES;
                     uint32_t ph = (kc / S::STAGES) & 1;
                     mbar_wait(&full[s], ph);
+                    if (SCHED == 1 && li == 0) mbar_wait(&b_full[kb], 0);
                     tc_fence_after();
                     if (tr && kb == kb0) tr[4] = clock64();
                     uint32_t sa = smem_u32(smem + s * S::STAGE_BYTES);
                     uint64_t da = make_smem_desc_sw128(sa);
-                    uint64_t db = make_smem_desc_sw128(sa + S::A_BYTES);
+                    uint64_t db = make_smem_desc_sw128(SCHED == 1 ? smem_u32(smem + S::BRES_OFF + kb * S::B_BYTES) : sa + S::A_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 16 elements (32 B) along K inside the 128-B swizzle atom: +2 in the (addr>>4) field;
@@ -280,14 +335,15 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int trow = quarter * 32 + lane;  // row inside the tile == TMEM lane
         const T* bias = reinterpret_cast<const T*>(p.bias);
         const T* res = reinterpret_cast<const T*>(p.residual);
-        const uint32_t epi = smem_u32(smem + S::EPI_OFF);
         const bool leader = warp == 2 && lane == 0;
         constexpr int PW = S::PW;
-        int li = 0;
-        for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
-            const int tile = item % (p.tiles_m * p.tiles_n), split = item / (p.tiles_m * p.tiles_n);
-            const int n0 = (tile % p.tiles_n) * BN;
-            const long m0 = (long)(tile / p.tiles_n) * BM;
+        for (int li = 0; li < walk.count; ++li) {
+            int split, m_tile, n_tile;
+            walk.at(p, li, split, m_tile, n_tile);
+            const int n0 = n_tile * BN;
+            const long m0 = (long)m_tile * BM;
+            // staging panels of this tile (EB = 2: tiles alternate between two sets)
+            const uint32_t epi = smem_u32(smem + S::EPI_OFF) + (uint32_t)(EB == 2 ? (li & 1) * S::EPI_BYTES : 0);
             const int buf = li % S::NBUF;
             const long m = m0 + trow;
             const bool row_ok = m < p.M;
@@ -334,7 +390,10 @@ gemm_tc_k(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const int hh = (ps & 1) ? half ^ 1 : half;  // the second pass swaps roles: 3 + 2 and 2 + 3 chunks per warp
                 if (!p.partial) {
                     if (ps > 0 && lean) prefetch(ps * PW + hh * 32);
-                    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous stores have read the panels
+                    if (leader) {  // the stores that last used these panels have read them
+                        if (EB == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
 #pragma unroll 1
@@ -555,6 +614,12 @@ bool gemm_tc_bn320_disabled() {
     return v;
 }
 
+// ETAI_GEMM_VARIANT is read on every call (a getenv is ~100 ns against a >= 5 us launch; graph replays do not come here)
+int gemm_tc_variant() {
+    const char* e = getenv("ETAI_GEMM_VARIANT");
+    return e ? atoi(e) : 0;
+}
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -566,31 +631,40 @@ int num_sms() {
     return n;
 }
 
-template <typename T, int BN, bool CONV>
+// B-stationary schedule: grid = groups x tiles_n CTAs, every group walks its own run of M tiles
+int bstat_groups(const TcParams& p) { return num_sms() / p.tiles_n; }
+
+template <typename T, int BN, bool CONV, int SCHED = 0, int EB = 1>
 void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const CUtensorMap& tmC2, const TcParams& p,
             cudaStream_t s) {
-    using S = Smem<BN>;
+    using S = Smem<BN, SCHED, EB>;
     static bool configured = false;
     if (!configured) {
-        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_k<T, BN, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+        CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_k<T, BN, CONV, SCHED, EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
         configured = true;
     }
     int items = p.tiles_m * p.tiles_n * p.splits;
     int grid = items < num_sms() ? items : num_sms();
+    if (SCHED == 1) grid = bstat_groups(p) * p.tiles_n;
     static const bool trace = [] { const char* e = getenv("ETAI_GEMM_TRACE"); return e && e[0] == '1'; }();
     if (trace) {  // debugging aid: synchronous, prints the mean per-tile timeline of CTA 0 and of all CTAs
         TcParams q = p;
         size_t n = (size_t)grid * TRACE_TILES * TRACE_SLOTS;
         CUDA_CHECK(cudaMalloc((void**)&q.trace, n * sizeof(long long)));
         CUDA_CHECK(cudaMemset(q.trace, 0, n * sizeof(long long)));
-        gemm_tc_k<T, BN, CONV><<<grid, GT_THREADS, S::TOTAL, s>>>(tmA, tmB, tmC, tmC2, q);
+        gemm_tc_k<T, BN, CONV, SCHED, EB><<<grid, GT_THREADS, S::TOTAL, s>>>(tmA, tmB, tmC, tmC2, q);
         CUDA_CHECK(cudaStreamSynchronize(s));
         std::vector<long long> h(n);
         CUDA_CHECK(cudaMemcpy(h.data(), q.trace, n * sizeof(long long), cudaMemcpyDeviceToHost));
         CUDA_CHECK(cudaFree(q.trace));
         double sum[6] = {0}; long cnt = 0;
         for (int c = 0; c < grid; ++c) {
-            int nt = (items - c + grid - 1) / grid; if (nt > TRACE_TILES) nt = TRACE_TILES;
+            int nt = (items - c + grid - 1) / grid;
+            if (SCHED == 1) {
+                const int ng = bstat_groups(p), g = c / p.tiles_n;
+                nt = (int)((long)(g + 1) * p.tiles_m / ng) - (int)((long)g * p.tiles_m / ng);
+            }
+            if (nt > TRACE_TILES) nt = TRACE_TILES;
             for (int t = 1; t + 1 < nt; ++t) {  // steady state: skip the first and the last tile
                 const long long* r = &h[((size_t)c * TRACE_TILES + t) * TRACE_SLOTS];
                 const long long* rn = r + TRACE_SLOTS;
@@ -604,12 +678,12 @@ void launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& t
             }
         }
         if (cnt)
-            printf("gemm_tc trace BN=%d conv=%d M=%ld N=%d kb=%d tiles/CTA=%.1f | cycles per tile: period %.0f, acc wait %.0f, "
-                   "first-kb wait %.0f, mainloop issue %.0f, epilogue %.0f, producer %.0f\n", BN, (int)CONV, p.M, p.N, p.num_kb,
-                   (double)items / grid, sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, sum[4] / cnt, sum[5] / cnt);
+            printf("gemm_tc trace BN=%d conv=%d sched=%d epi_bufs=%d stages=%d M=%ld N=%d kb=%d geglu=%d tiles/CTA=%.1f | cycles per tile: "
+                   "period %.0f, acc wait %.0f, first-kb wait %.0f, mainloop issue %.0f, epilogue %.0f, producer %.0f\n", BN,
+                   (int)CONV, SCHED, EB, S::STAGES, p.M, p.N, p.num_kb, p.geglu, (double)items / grid, sum[0] / cnt, sum[1] / cnt, sum[2] / cnt, sum[3] / cnt, sum[4] / cnt, sum[5] / cnt);
         return;
     }
-    gemm_tc_k<T, BN, CONV><<<grid, GT_THREADS, S::TOTAL, s>>>(tmA, tmB, tmC, tmC2, p);
+    gemm_tc_k<T, BN, CONV, SCHED, EB><<<grid, GT_THREADS, S::TOTAL, s>>>(tmA, tmB, tmC, tmC2, p);
     KERNEL_CHECK();
     if (p.partial) {
         long total = p.M * p.N / 4;
@@ -660,15 +734,18 @@ void gemm_tc(const GemmArgs& a0, void* ws, size_t ws_bytes, cudaStream_t s) {
     p.C = a.C; p.bias = a.bias; p.bias2 = (const float*)a.rowbias; p.residual = a.residual;
     p.M = a.M; p.N = a.N; p.ldc = a.ldc; p.ldr = a.ldr; p.geglu = a.geglu;
     p.fmt = a.dtype == ETAI_BF16 ? 1 : 0;
-    // Tile width.  One SM's TMA unit delivers a 128-byte operand row every ~1.7 cycles (scripts/ubench/tma_rate.cu,
-    // profiles/r02_tma_rate.txt), so a 128 x 160 tile (288 rows per k-block for 320 MMA cycles) is TMA-bound at ~60 % of the
-    // tensor pipe; 128 x 320 (448 rows for 640 MMA cycles) loads A once per 320 columns.  It is used when it still fills
-    // the SMs (or split-K will).
+    // Tile width.  The main loop of a 128 x 160 tile costs ~600 cycles per 64-wide k-block against 320 cycles of tensor-pipe
+    // work, and that does not change when TMA moves 128 instead of 288 operand rows per k-block (the B-stationary schedule,
+    // profiles/r02_gemm_role_trace.txt): operand delivery is not what paces it.  What fits the measurements is the shared-
+    // memory port: an SS-mode UMMA fetches A and B from shared memory for every instruction (9 KB per 128 x 160 x 16, ~96 cycles
+    // measured in isolation, profiles/r01_ubench_umma_latency.txt) while TMA writes and the epilogue's staging traffic use the
+    // same 128 B/clk.  A 128 x 320 tile (two accumulators) amortises better per column and is used when it still fills the
+    // SMs (or split-K will).
     p.tiles_m = cdiv(a.M, BM);
     int BN = (a.N % 160 == 0) ? 160 : 128;
     if (a.N % 320 == 0 && !gemm_tc_bn320_disabled()) {
-        // Cost model in SM cycles per CTA, fitted to profiles/r02_ops_*.txt (M = 4096..65536, K = 320..5120): a 128 x 160
-        // tile costs ~590 cycles per k-block (TMA-bound) + ~3000 per tile; a 128 x 320 tile ~930 per k-block + ~9900 per tile
+        // Cost model in SM cycles per CTA, fitted to profiles/r02_bench_ops_all.txt (M = 4096..65536, K = 320..5120): a 128 x 160
+        // tile costs ~590 cycles per k-block + ~3000 per tile; a 128 x 320 tile ~930 per k-block + ~9900 per tile
         // (its accumulators are single-buffered, so the epilogue is exposed).  Per unit of work the wide tile wins from
         // K ~ 1000 on -- every conv3x3 (K >= 2880) and the K >= 1280 projections -- unless wave quantisation says otherwise.
         const long t320 = (long)p.tiles_m * (a.N / 320), t160 = 2 * t320;
@@ -733,14 +810,30 @@ void gemm_tc(const GemmArgs& a0, void* ws, size_t ws_bytes, cudaStream_t s) {
             p.partial = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + ws_used);
         }
     }
+    // Kernel variant (ETAI_GEMM_VARIANT, bit mask; results are bit-identical across variants, only the schedule differs):
+    //   bit 0: two epilogue staging buffers for the 128 / 160-wide tiles;
+    //   bit 1: B-stationary schedule for the dense K <= 320 projections at N % 160 == 0 when every group gets M tiles.
+    // Both are opt-in experiments: measured on a B200 (profiles/r02_gemm_variants_ab.txt) they are bit-identical to the
+    // default on every production shape and worth 0-7 % per shape, ~1 % over the UNet's dense GEMMs -- the default stays.
+    const int variant = gemm_tc_variant();
+    const bool eb2 = (variant & 1) && BN != 320;
+    const bool bstat = (variant & 2) && BN == 160 && !a.conv && p.splits == 1 && p.num_kb <= 5 &&
+                       p.tiles_n * 2 <= num_sms() && p.tiles_m >= 2 * bstat_groups(p);
 #define LAUNCH(T)                                                            \
     do {                                                                     \
         if (BN == 320) {                                                     \
             if (a.conv) launch<T, 320, true>(tmA, tmB, tmC, tmC2, p, s);           \
             else launch<T, 320, false>(tmA, tmB, tmC, tmC2, p, s);                 \
         } else if (BN == 160) {                                              \
-            if (a.conv) launch<T, 160, true>(tmA, tmB, tmC, tmC2, p, s);           \
+            if (bstat) launch<T, 160, false, 1, 1>(tmA, tmB, tmC, tmC2, p, s);     \
+            else if (eb2) {                                                  \
+                if (a.conv) launch<T, 160, true, 0, 2>(tmA, tmB, tmC, tmC2, p, s);  \
+                else launch<T, 160, false, 0, 2>(tmA, tmB, tmC, tmC2, p, s);        \
+            } else if (a.conv) launch<T, 160, true>(tmA, tmB, tmC, tmC2, p, s);     \
             else launch<T, 160, false>(tmA, tmB, tmC, tmC2, p, s);                 \
+        } else if (eb2) {                                                    \
+            if (a.conv) launch<T, 128, true, 0, 2>(tmA, tmB, tmC, tmC2, p, s);      \
+            else launch<T, 128, false, 0, 2>(tmA, tmB, tmC, tmC2, p, s);            \
         } else {                                                             \
             if (a.conv) launch<T, 128, true>(tmA, tmB, tmC, tmC2, p, s);           \
             else launch<T, 128, false>(tmA, tmB, tmC, tmC2, p, s);                 \

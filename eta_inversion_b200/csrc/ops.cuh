@@ -170,5 +170,9 @@ void cfg_ddim_step(const float* eps, int n, int has_cfg, float guidance, const f
 void eta_noise_losses(const float* eps, int n, int has_cfg, float guidance, const float* x, const float* x_prev_inv,
                       float a_from, float a_to, float eta, float variance, const float* noise_cand, int K, long E,
                       float* losses, int* best_idx, cudaStream_t s);
+// out = eps_u + guidance * prox(eps_c - eps_u): soft threshold at a global quantile of |eps_c - eps_u| (rank_lo >= 0: torch
+// 'linear' interpolation between order statistics rank_lo / rank_hi with `weight`) or at fixed_thr (rank_lo < 0)
+void prox_guidance(const float* eps_u, const float* eps_c, float* out, long n, long rank_lo, long rank_hi, float weight,
+                   float fixed_thr, int l1, float guidance, float* thr_out, cudaStream_t s);
 
 }  // namespace etai

@@ -414,6 +414,42 @@ def cfg_ddim_step(eps, x, a_from: float, a_to: float, guidance: Optional[float] 
     return (out, eps_out) if want_eps else out
 
 
+def prox_guidance(eps_u: torch.Tensor, eps_c: torch.Tensor, guidance: float, quantile: float, l1: bool = False,
+                  want_thr: bool = False):
+    """eps_u + guidance * prox(eps_c - eps_u), the soft threshold taken at ``quantile`` of |eps_c - eps_u| over the whole
+    tensor (torch.quantile's 'linear' rule) or, for ``quantile <= 0``, at the fixed value ``-quantile``; one launch
+    (include/etai.h etai_prox_guidance; reference: proximal_negative_prompt_inversion.py:61-128)."""
+    for n_, t in (("eps_u", eps_u), ("eps_c", eps_c)):
+        _require_cuda(t, n_)
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise RuntimeError("etai: prox_guidance takes contiguous fp32 tensors")
+    if eps_u.shape != eps_c.shape:
+        raise RuntimeError("etai: prox_guidance: shape mismatch")
+    n = eps_u.numel()
+    lo, hi, w, fixed = -1, -1, 0.0, 0.0
+    if quantile > 0:
+        lo, hi, w = quantile_ranks(quantile, n)
+    else:
+        fixed = -float(quantile)
+    out = torch.empty_like(eps_u)
+    thr = torch.empty((1,), dtype=torch.float32, device=eps_u.device) if want_thr else None
+    check(_lib.load().etai_prox_guidance(ptr(eps_u), ptr(eps_c), ptr(out), n, lo, hi, w, fixed, int(bool(l1)), float(guidance),
+                                         ptr(thr), stream_ptr()))
+    _count_launches(1)
+    return (out, thr) if want_thr else out
+
+
+def quantile_ranks(q: float, n: int):
+    """(rank_lo, rank_hi, weight) of torch.quantile(x, q) with 'linear' interpolation over n elements: torch multiplies a
+    float32 q by the last index in float32 and interpolates between floor and ceil of that rank (ATen quantile_compute)."""
+    import numpy as np
+    if not 0.0 <= q <= 1.0:
+        raise RuntimeError("etai: quantile must be in [0, 1]")
+    r = np.float32(q) * np.float32(n - 1)
+    lo, hi = int(np.floor(r)), int(np.ceil(r))
+    return lo, hi, float(np.float32(r) - np.float32(lo))
+
+
 def eta_noise_losses(eps, x, x_prev_inv, a_from: float, a_to: float, guidance: Optional[float], eta: float,
                      variance: float, noise_cand: torch.Tensor):
     n = x.shape[0]

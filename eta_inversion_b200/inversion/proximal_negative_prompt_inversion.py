@@ -4,8 +4,9 @@ Negative-prompt inversion whose denoising CFG uses a proximally-thresholded scor
   delta = eps_cond - eps_uncond ;  thr = quantile_q(|delta|) over the whole tensor (or -q if q < 0)
   l0: delta -= clamp(delta, -thr, thr)            l1: additionally shrink the survivors by thr
   eps = eps_uncond + g * delta
-The UNet forward and the DDIM step are the native kernels; the threshold selection (a global quantile over 2x16384
-values) is a handful of device-side torch ops between them (no host sync).  The reconstruction-guidance branch of the
+The UNet forward and the DDIM step are the native kernels, and so is the proximal CFG itself: ``etai_prox_guidance`` finds
+the global quantile (over 2x16384 values) by radix select and applies threshold + guidance in the same launch (no sort, no
+host sync; csrc/elementwise.cu).  The reconstruction-guidance branch of the
 upstream ProxNPI is dead code in the reference (it asserts ref_image is None) and is not reproduced."""
 from __future__ import annotations
 
@@ -13,6 +14,7 @@ from typing import Optional
 
 import torch
 
+from .. import engine as E
 from .negative_prompt_inversion import NegativePromptInversion
 
 
@@ -31,13 +33,8 @@ class ProximalNegativePromptInversion(NegativePromptInversion):
             return noise_pred_uncond + guidance_scale * (noise_prediction_text - noise_pred_uncond)
         if self.prox not in ("l0", "l1"):
             raise NotImplementedError
-        delta = noise_prediction_text - noise_pred_uncond
-        thr = delta.abs().float().quantile(self.quantile) if self.quantile > 0 else -self.quantile
-        delta = delta - delta.clamp(-thr, thr)
-        if self.prox == "l1":
-            delta = torch.where(delta > 0, delta - thr, delta)
-            delta = torch.where(delta < 0, delta + thr, delta)
-        return noise_pred_uncond + guidance_scale * delta
+        return E.prox_guidance(noise_pred_uncond.float().contiguous(), noise_prediction_text.float().contiguous(),
+                               float(guidance_scale), float(self.quantile), l1=self.prox == "l1")
 
     def _unet_eps(self, latent, t, context, guidance_scale, is_fwd: bool = False):
         # always the full [uncond, cond] batch (reference :130-150); the proximal CFG is applied here for denoising steps

@@ -251,6 +251,17 @@ ETAI_EXPORT int etai_eta_noise_losses(const float* eps, int32_t n, int32_t has_c
                           const float* noise_cand, int32_t K, int64_t E, float* losses, int32_t* best_idx,
                           void* stream);
 
+/* Proximal CFG of proximal negative-prompt inversion (proximal_negative_prompt_inversion.py:61-128, prox = "l0" | "l1"):
+ *   delta = eps_c - eps_u;  thr = quantile_q(|delta|) over all n elements;  delta -= clamp(delta, -thr, thr);
+ *   l1: delta = where(delta > 0, delta - thr, delta); delta = where(delta < 0, delta + thr, delta);
+ *   out = eps_u + guidance * delta.
+ * The quantile is torch.quantile's 'linear' rule: with r = float32(q) * float32(n - 1), rank_lo = floor(r), rank_hi = ceil(r),
+ * weight = r - rank_lo, thr = lerp(sorted[rank_lo], sorted[rank_hi], weight) -- found by radix select, no sort.
+ * rank_lo < 0 selects the fixed threshold `fixed_thr` (the reference's negative `quantile`).  thr_out: device float[1] or
+ * NULL.  One launch, no host sync; all buffers fp32; out must not alias the inputs. */
+ETAI_EXPORT int etai_prox_guidance(const float* eps_u, const float* eps_c, float* out, int64_t n, int64_t rank_lo, int64_t rank_hi,
+                       float weight, float fixed_thr, int32_t l1, float guidance, float* thr_out, void* stream);
+
 /* ---- single ops, exported for unit parity and roofline runs ------------------------------------- */
 /* y = SiLU?(GroupNorm(x)) over NHWC x:[B,HW,C] */
 ETAI_EXPORT int etai_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int32_t B, int64_t HW, int32_t C,

@@ -231,3 +231,18 @@ def test_tensor_table_converts_plain_tensors_on_the_host():
     assert got["ids"][1].dtype == torch.float16            # integer tensors are widened to float first, then plain
     arr32, keep32 = _lib.tensor_table(sd)                    # no storage dtype: nothing is converted
     assert all(k.dtype == torch.float32 for k in keep32)
+
+
+def test_quantile_ranks_reproduce_torch_quantile():
+    """engine.quantile_ranks feeds etai_prox_guidance: lerp(sorted[lo], sorted[hi], w) must be torch.quantile's 'linear'
+    result bit for bit (float32 rank arithmetic of ATen's quantile_compute), including integer ranks and both ends."""
+    import torch
+    from eta_inversion_b200.engine import quantile_ranks
+    g = torch.Generator().manual_seed(0)
+    for n in (7, 100, 1000, 16384, 32768, 49152):
+        x = torch.randn(n, generator=g).abs()
+        s = x.sort().values
+        for q in (0.0, 0.0001, 0.25, 0.3, 0.5, 0.7, 0.999, 1.0):
+            lo, hi, w = quantile_ranks(q, n)
+            assert 0 <= lo <= hi <= min(lo + 1, n - 1) and 0.0 <= w < 1.0
+            assert torch.lerp(s[lo], s[hi], torch.tensor(w)) == x.quantile(q), (n, q)

@@ -308,6 +308,43 @@ def test_scheduler_step_matches_closed_form():
     assert (back - x).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize("shape,q,l1,dup", [((2, 4, 64, 64), 0.7, False, False), ((1, 4, 64, 64), 0.7, True, False),
+                                           ((2, 4, 64, 64), 0.5, False, True), ((1, 1000), 0.999, True, False),
+                                           ((3, 4, 64, 64), 0.0001, False, False), ((1, 4, 64, 64), 1.0, False, False),
+                                           ((2, 4, 64, 64), -0.05, True, False), ((1, 7), 0.3, False, True)])
+def test_prox_guidance_matches_torch_quantile(shape, q, l1, dup):
+    """etai_prox_guidance (radix select + soft threshold + guidance in one launch) against the reference's torch lines
+    (proximal_negative_prompt_inversion.py:84-113): same threshold as torch.quantile -- the same order statistics and the
+    same float32 rank arithmetic -- and the same thresholded CFG output."""
+    from eta_inversion_b200 import engine as E
+    u, c = _rand(shape, 11).cuda(), _rand(shape, 12).cuda()
+    if dup:  # many equal |delta| values: the successor search must step over the run of duplicates
+        u, c = (u * 4).round() / 4, (c * 4).round() / 4
+    g = 7.5
+    out, thr = E.prox_guidance(u, c, g, q, l1=l1, want_thr=True)
+    delta = c - u
+    thr_ref = delta.abs().quantile(q) if q > 0 else torch.tensor(-q, device="cuda")
+    assert torch.allclose(thr[0], thr_ref.float(), rtol=1e-6, atol=0), (thr.item(), thr_ref.item())
+    t = thr[0]  # the thresholding itself is compared at the kernel's own threshold (a 1-ulp lerp difference moves no element)
+    d = delta - delta.clamp(-t, t)
+    if l1:
+        d = torch.where(d > 0, d - t, d)
+        d = torch.where(d < 0, d + t, d)
+    ref = u + g * d
+    assert torch.equal(out, ref)
+    if q > 0 and not dup:  # the fraction of surviving elements is what the quantile promises
+        frac = (d != 0).float().mean().item()
+        assert abs(frac - (1 - q)) <= 2.0 / delta.numel() + (0.02 if l1 else 0.0)
+
+
+def test_prox_guidance_nan_propagates():
+    from eta_inversion_b200 import engine as E
+    u, c = _rand((1, 4, 64, 64), 1).cuda(), _rand((1, 4, 64, 64), 2).cuda()
+    c[0, 1, 2, 3] = float("nan")
+    out, thr = E.prox_guidance(u, c, 7.5, 0.7, want_thr=True)
+    assert torch.isnan(thr).all() and torch.isnan(out).all()  # torch.quantile returns NaN, clamp(NaN bounds) spreads it
+
+
 def test_ddim_step_stochastic_rows_get_independent_noise():
     """DDIMScheduler.step(eta > 0, variance_noise=None) with B > 1: diffusers draws randn of the SAMPLE's shape, so every row
     has its own noise; an explicit per-row variance_noise [B,C,H,W] is honoured row by row."""
