@@ -12,12 +12,36 @@ stay per lane, so results equal the sequential ones (bit-exact on the fp32 path,
 from __future__ import annotations
 
 import copy
+import sys
 import threading
 from typing import Any, Callable, Dict, List, Optional, Sequence
 
 import torch
 
 from .engine import AttnControl, UNetEngine, UNetOutput
+
+
+class _FastGilSwitch:
+    """Lanes hand the GIL over at every rendez-vous; the interpreter's 5 ms default switch interval stalls the others.
+    The setting is process-wide and groups run concurrently (run_pipelined), so it is reference-counted: the first group in
+    shortens it, the last one out restores what it found."""
+
+    _lock, _users, _saved = threading.Lock(), 0, None
+
+    def __enter__(self):
+        cls = _FastGilSwitch
+        with cls._lock:
+            if cls._users == 0:
+                cls._saved = sys.getswitchinterval()
+                sys.setswitchinterval(2e-4)
+            cls._users += 1
+
+    def __exit__(self, *exc):
+        cls = _FastGilSwitch
+        with cls._lock:
+            cls._users -= 1
+            if cls._users == 0:
+                sys.setswitchinterval(cls._saved)
 
 
 class _LaneUNet:
@@ -238,16 +262,11 @@ def run_lockstep(pipe, jobs: Sequence[Dict[str, Any]], make_editor: Callable[[An
             group.abort()
 
     threads = [threading.Thread(target=work, args=(l,), name=f"etai-lane-{l}") for l in range(k)]
-    import sys
-    old_interval = sys.getswitchinterval()
-    sys.setswitchinterval(2e-4)  # lanes hand the GIL over at every rendez-vous; the 5 ms default stalls the others
-    try:
+    with _FastGilSwitch():
         for th in threads:
             th.start()
         for th in threads:
             th.join()
-    finally:
-        sys.setswitchinterval(old_interval)
     for e in errors:  # the root cause first: lanes that were merely aborted report "group aborted"
         if e is not None and "group aborted" not in str(e):
             raise e

@@ -178,3 +178,20 @@ def test_merge_role_major_for_plug_and_play():
     assert ctrl.conv_inject_rows == 2
     # stub: eps = sample + merged row index -> lane 0 rows 0, 2, 4 ; lane 1 rows 1, 3, 5
     assert outs[0][:, 0, 0, 0].tolist() == [0.0, 3.0, 6.0] and outs[1][:, 0, 0, 0].tolist() == [11.0, 14.0, 17.0]
+
+
+def test_gil_switch_interval_is_restored_after_overlapping_groups():
+    """run_lockstep shortens the interpreter's switch interval while lanes run; groups overlap in run_pipelined, so the
+    process-wide setting is reference-counted: inner exits must not restore early, the last exit restores the original."""
+    import sys
+    from eta_inversion_b200.batching import _FastGilSwitch
+    before = sys.getswitchinterval()
+    a, b = _FastGilSwitch(), _FastGilSwitch()
+    a.__enter__()
+    fast = sys.getswitchinterval()
+    assert fast < before
+    b.__enter__()
+    a.__exit__(None, None, None)
+    assert sys.getswitchinterval() == fast       # group b is still running
+    b.__exit__(None, None, None)
+    assert sys.getswitchinterval() == before
