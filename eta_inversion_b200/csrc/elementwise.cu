@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(PROX_THREADS) prox_guidance_k(const float* __r
             const unsigned prefix = s_prefix;
             for (long e = tid; e < n; e += PROX_THREADS) {
                 const float d = fabsf(c[e] - u[e]);
-                if (d != d) s_nan = 1u;  // torch.quantile returns NaN when any element is NaN
+                if (d != d) atomicOr(&s_nan, 1u);  // torch.quantile returns NaN when any element is NaN
                 const unsigned key = __float_as_uint(d);
                 if ((key & mask) == prefix) atomicAdd(&hist[warp][(key >> shift) & 255u], 1u);
             }
