@@ -70,6 +70,7 @@ SYMBOLS = {
     "etai_unet_clone": (C.c_int, [C.POINTER(_vp), _vp, _i32]),
     "etai_unet_set_context": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "etai_unet_forward": (C.c_int, [_vp, _vp, _f, _i32, _i32, C.POINTER(EtaiAttnCtrl), _vp, _vp]),
+    "etai_unet_forward_rows": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), _i32, _i32, C.POINTER(EtaiAttnCtrl), _vp, _vp]),
     "etai_unet_enable_backward": (C.c_int, [_vp, _i32]),
     "etai_unet_forward_train": (C.c_int, [_vp, _vp, _f, _i32, _i32, _vp, _vp]),
     "etai_unet_backward_ctx": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),

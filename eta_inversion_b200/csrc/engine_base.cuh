@@ -239,14 +239,17 @@ struct OpCtx {
     }
     // pad = 1: the usual pad-1 conv; pad = 0 with stride 2: zero padding on the right / bottom only (AutoencoderKL's
     // downsampler, F.pad(x, (0,1,0,1)) + conv(stride 2, padding 0))
+    // rowbias: fp32 bias added per (row group, n): one vector for all rows (rows_per_group = 0 -> M) or a
+    // [M / rows_per_group, ldrb] table (one row of it per image when rows_per_group = Ho * Wo)
     void* conv3x3(const void* x, int B, int H, int W, const Conv& c, int stride, const float* rowbias,
-                  const void* residual, cudaStream_t s, void* out = nullptr, int pad = 1) {
+                  const void* residual, cudaStream_t s, void* out = nullptr, int pad = 1, long rows_per_group = 0,
+                  long ldrb = 0) {
         int Ho = (H + 1 + pad - 3) / stride + 1, Wo = (W + 1 + pad - 3) / stride + 1;
         long M = (long)B * Ho * Wo;
         void* y = out ? out : arena.alloc((size_t)M * c.cout * esz);
         GemmArgs a;
         a.A = x; a.W = c.w; a.C = y; a.bias = c.b; a.residual = residual; a.rowbias = rowbias;
-        a.rows_per_group = M; a.ldrb = 0;
+        a.rows_per_group = rows_per_group > 0 ? rows_per_group : M; a.ldrb = rows_per_group > 0 ? ldrb : 0;
         a.M = M; a.N = c.cout; a.K = 9 * c.cin; a.ldc = c.cout; a.ldr = c.cout;
         a.conv = 1; a.B = B; a.H = H; a.Wd = W; a.Cin = c.cin; a.stride = stride; a.Ho = Ho; a.Wo = Wo; a.pad = pad;
         a.dtype = dt;

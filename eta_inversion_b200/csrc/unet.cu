@@ -55,6 +55,10 @@ struct etai_unet : etai::OpCtx {
     char* in_stage = nullptr;           // latent  [max_batch,4,hw,hw] (io dtype, <= 4 bytes/elem)
     char* out_stage = nullptr;          // eps out
     float* t_dev = nullptr;
+    // one timestep per batch row (etai_unet_forward_rows): per-row copies of the time-embedding scratch, made on first use
+    float* tbuf_rows = nullptr;
+    const float* t_rows_host = nullptr;  // non-null only inside a mixed-timestep forward()
+    size_t tb_stride() const { return (size_t)(TB_PROJ + temb_total + 64); }
     float *c_mapper = nullptr, *c_blend = nullptr, *c_eq = nullptr, *c_alpha = nullptr;  // staged PtP tables
     float* c_store[3] = {nullptr, nullptr, nullptr};  // per-forward attention-store sums per place
     bool use_graphs = true;
@@ -155,7 +159,11 @@ struct etai_unet : etai::OpCtx {
                  cudaStream_t s) {
         long HW = (long)H * W, M = B * HW;
         void* a1 = gnorm(x, B, HW, r.n1, 1e-5f, true, s);
-        void* h = conv3x3(a1, B, H, W, r.c1, 1, tbuf + TB_PROJ + r.temb_off, nullptr, s);
+        // time-embedding bias: one fp32 vector for all rows (fused by the tcgen05 epilogue) or, with one timestep per row,
+        // a [B, cout] table applied per image (rows_per_group = HW; the SIMT conv serves that case)
+        void* h = t_rows_host
+                      ? conv3x3(a1, B, H, W, r.c1, 1, tbuf_rows + TB_PROJ + r.temb_off, nullptr, s, nullptr, 1, HW, (long)tb_stride())
+                      : conv3x3(a1, B, H, W, r.c1, 1, tbuf + TB_PROJ + r.temb_off, nullptr, s);
         void* a2 = gnorm(h, B, HW, r.n2, 1e-5f, true, s);
         const void* skip = x;
         if (r.has_sc) skip = linear(x, M, r.sc, nullptr, s);
@@ -368,7 +376,17 @@ void etai_unet::run_body(int io_dtype, int B, const etai_attn_ctrl* ctrl, cudaSt
     arena.reset();
 
     // time embedding (t is shared by all rows): all fp32, M = 1 skinny GEMMs
-    if (!planning) {
+    if (!planning && t_rows_host) {  // one timestep per row: B independent M = 1 chains into the per-row scratch
+        cudaEvent_t e = prof_begin(s);
+        for (int b = 0; b < B; ++b) {
+            float* tb = tbuf_rows + (size_t)b * tb_stride();
+            timestep_sincos(t_dev + b, tb + TB_SIN, c[0], s);
+            skinny_linear(tb + TB_SIN, time1.w, time1.b, tb + TB_H1, 1, temb, c[0], 1, dt, s);
+            skinny_linear(tb + TB_H1, time2.w, time2.b, tb + TB_ST, 1, temb, temb, 1, dt, s);
+            skinny_linear(tb + TB_ST, temb_all.w, temb_all.b, tb + TB_PROJ, 1, temb_all.n, temb, 0, dt, s);
+        }
+        prof_end(ETAI_PROF_OTHER, e, 4 * B, s);
+    } else if (!planning) {
         cudaEvent_t e = prof_begin(s);
         timestep_sincos(t_dev, tbuf + TB_SIN, c[0], s);
         skinny_linear(tbuf + TB_SIN, time1.w, time1.b, tbuf + TB_H1, 1, temb, c[0], 1, dt, s);        // silu(linear_1)
@@ -500,7 +518,9 @@ void etai_unet::forward(const void* latent, float t, int io_dtype, int B, const 
     CUDA_CHECK(cudaStreamWaitEvent(gs, ev_in, 0));
     // ---- prologue: stage every per-call input at a stable address ----
     CUDA_CHECK(cudaMemcpyAsync(in_stage, latent, io_bytes, cudaMemcpyDeviceToDevice, gs));
-    CUDA_CHECK(cudaMemcpyAsync(t_dev, &t, sizeof(float), cudaMemcpyHostToDevice, gs));  // pageable 4-byte copy: staged by the driver
+    // pageable copy of a few bytes: staged by the driver before the call returns
+    if (t_rows_host) CUDA_CHECK(cudaMemcpyAsync(t_dev, t_rows_host, (size_t)B * sizeof(float), cudaMemcpyHostToDevice, gs));
+    else CUDA_CHECK(cudaMemcpyAsync(t_dev, &t, sizeof(float), cudaMemcpyHostToDevice, gs));
     etai_attn_ctrl ic;
     const etai_attn_ctrl* body_ctrl = nullptr;
     if (ctrl) {
@@ -539,7 +559,7 @@ void etai_unet::forward(const void* latent, float t, int io_dtype, int B, const 
         done = true;
     }
     if (!done && use_graphs && !prof_on) {
-        GraphEntry& ge = graphs[graph_key(io_dtype, B, ctrl)];
+        GraphEntry& ge = graphs[graph_key(io_dtype, B, ctrl) + (t_rows_host ? "R" : "")];
         if (ge.exec) {
             CUDA_CHECK(cudaGraphLaunch(ge.exec, gs));
             launches += ge.launches;
@@ -1022,6 +1042,7 @@ int etai_unet_destroy(etai_unet* h) {
     if (h->kv_cache) cudaFree(h->kv_cache);
     if (h->ctx_buf) cudaFree(h->ctx_buf);
     if (h->tbuf) cudaFree(h->tbuf);
+    if (h->tbuf_rows) cudaFree(h->tbuf_rows);
     if (h->gn_ws) cudaFree(h->gn_ws);
     for (auto& kv : h->graphs)
         if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
@@ -1112,23 +1133,52 @@ int etai_unet_set_context(etai_unet* h, const void* ctx, int32_t io_dtype, int32
     ETAI_API_END
 }
 
+static void check_ctrl(const etai_attn_ctrl* ctrl) {
+    if (!ctrl) return;
+    if (ctrl->flags & ETAI_CTRL_SELF_REMAP)
+        ETAI_CHECK(ctrl->self_q_row && ctrl->self_k_row && ctrl->self_v_row, ETAI_ERR_ARG, "ctrl: self remap arrays");
+    if (ctrl->flags & ETAI_CTRL_CROSS_EDIT)
+        ETAI_CHECK(ctrl->n_pairs >= 1 && ctrl->n_pairs <= ETAI_MAX_PAIRS && ctrl->edit_base_row && ctrl->edit_tgt_row &&
+                       ctrl->mapper && ctrl->blend_a && ctrl->equalizer && ctrl->alpha_step,
+                   ETAI_ERR_ARG, "ctrl: cross edit tables");
+    if (ctrl->flags & ETAI_CTRL_CROSS_STORE)
+        ETAI_CHECK(ctrl->store_res > 0 && ctrl->n_store_rows >= 1 && ctrl->n_store_rows <= ETAI_MAX_ROWS && ctrl->store_row,
+                   ETAI_ERR_ARG, "ctrl: store rows");
+}
+
 int etai_unet_forward(etai_unet* h, const void* latent, float t, int32_t io_dtype, int32_t B,
                       const etai_attn_ctrl* ctrl, void* eps_out, void* stream) {
     ETAI_API_BEGIN
     ETAI_CHECK(h && latent && eps_out, ETAI_ERR_ARG, "forward: null argument");
     CUDA_CHECK(cudaSetDevice(h->device));
-    if (ctrl) {
-        if (ctrl->flags & ETAI_CTRL_SELF_REMAP)
-            ETAI_CHECK(ctrl->self_q_row && ctrl->self_k_row && ctrl->self_v_row, ETAI_ERR_ARG, "ctrl: self remap arrays");
-        if (ctrl->flags & ETAI_CTRL_CROSS_EDIT)
-            ETAI_CHECK(ctrl->n_pairs >= 1 && ctrl->n_pairs <= ETAI_MAX_PAIRS && ctrl->edit_base_row && ctrl->edit_tgt_row &&
-                           ctrl->mapper && ctrl->blend_a && ctrl->equalizer && ctrl->alpha_step,
-                       ETAI_ERR_ARG, "ctrl: cross edit tables");
-        if (ctrl->flags & ETAI_CTRL_CROSS_STORE)
-            ETAI_CHECK(ctrl->store_res > 0 && ctrl->n_store_rows >= 1 && ctrl->n_store_rows <= ETAI_MAX_ROWS && ctrl->store_row,
-                       ETAI_ERR_ARG, "ctrl: store rows");
-    }
+    check_ctrl(ctrl);
     h->forward(latent, t, io_dtype, B, ctrl, eps_out, (cudaStream_t)stream);
+    ETAI_API_END
+}
+
+int etai_unet_forward_rows(etai_unet* h, const void* latent, const float* t_rows, int32_t io_dtype, int32_t B,
+                           const etai_attn_ctrl* ctrl, void* eps_out, void* stream) {
+    ETAI_API_BEGIN
+    ETAI_CHECK(h && latent && eps_out && t_rows, ETAI_ERR_ARG, "forward_rows: null argument");
+    ETAI_CHECK(B >= 1 && B <= h->cfg.max_batch && B <= 64, ETAI_ERR_ARG, "forward_rows: batch out of range");
+    CUDA_CHECK(cudaSetDevice(h->device));
+    check_ctrl(ctrl);
+    bool same = true;
+    for (int b = 1; b < B; ++b) same = same && t_rows[b] == t_rows[0];
+    if (same) {  // the usual case (every loop of the reference): the shared-bias schedule and its CUDA graphs
+        h->forward(latent, t_rows[0], io_dtype, B, ctrl, eps_out, (cudaStream_t)stream);
+    } else {
+        if (!h->tbuf_rows)
+            CUDA_CHECK(cudaMalloc((void**)&h->tbuf_rows, (size_t)h->cfg.max_batch * h->tb_stride() * sizeof(float)));
+        h->t_rows_host = t_rows;
+        try {
+            h->forward(latent, t_rows[0], io_dtype, B, ctrl, eps_out, (cudaStream_t)stream);
+        } catch (...) {
+            h->t_rows_host = nullptr;
+            throw;
+        }
+        h->t_rows_host = nullptr;
+    }
     ETAI_API_END
 }
 

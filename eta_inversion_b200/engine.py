@@ -235,7 +235,15 @@ class UNetEngine:
             k = self._ctx_key
             if k is None or k[0] is not ctx or k[1] != ctx._version:  # constant over a loop: re-project only on change
                 self.set_context(ctx)
-        t = float(timestep.item() if torch.is_tensor(timestep) else timestep)
+        # diffusers takes a scalar or a [B] tensor of timesteps; the reference's loops only ever pass scalars
+        t_rows = None
+        if (torch.is_tensor(timestep) and timestep.numel() > 1) or isinstance(timestep, (list, tuple)):
+            t_rows = [float(v) for v in (timestep.flatten().tolist() if torch.is_tensor(timestep) else timestep)]
+            if len(t_rows) != B:
+                raise RuntimeError(f"etai: {len(t_rows)} timesteps for {B} rows")
+            t = t_rows[0]
+        else:
+            t = float(timestep.item() if torch.is_tensor(timestep) else timestep)
         ctrl = control if control is not None else self.control
         out = torch.empty_like(sample)
         cs = ctrl.to_struct() if ctrl is not None else None
@@ -243,8 +251,12 @@ class UNetEngine:
             if self._timing is not None:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            check(self._lib.etai_unet_forward(self._h, ptr(sample), t, dtype_code(sample.dtype), B,
-                                              C.byref(cs) if cs is not None else None, ptr(out), stream_ptr()))
+            if t_rows is not None:
+                check(self._lib.etai_unet_forward_rows(self._h, ptr(sample), (C.c_float * B)(*t_rows), dtype_code(sample.dtype), B,
+                                                       C.byref(cs) if cs is not None else None, ptr(out), stream_ptr()))
+            else:
+                check(self._lib.etai_unet_forward(self._h, ptr(sample), t, dtype_code(sample.dtype), B,
+                                                  C.byref(cs) if cs is not None else None, ptr(out), stream_ptr()))
             if self._timing is not None:
                 ev[1].record()
                 self._timing.append(ev)

@@ -152,6 +152,14 @@ ETAI_EXPORT int etai_unet_set_context(etai_unet* h, const void* ctx, int32_t io_
 ETAI_EXPORT int etai_unet_forward(etai_unet* h, const void* latent, float t, int32_t io_dtype, int32_t B,
                       const etai_attn_ctrl* ctrl, void* eps_out, void* stream);
 
+/* The same with one timestep per batch row -- diffusers' UNet accepts a [B] timestep tensor ("t scalar
+ * or [B]"), although every loop of the reference passes a scalar.  t_rows: HOST array of B floats.  When all B values are
+ * equal this IS etai_unet_forward (same schedule, same CUDA graphs).  Otherwise every row gets its own time embedding and the
+ * 22 resnets add a per-image [B, Cout] time bias: the tcgen05 conv epilogue fuses one shared vector only, so those 22 convs
+ * run on the fp32-accumulating SIMT conv and a mixed-timestep forward is slower than a uniform one. */
+ETAI_EXPORT int etai_unet_forward_rows(etai_unet* h, const void* latent, const float* t_rows, int32_t io_dtype, int32_t B,
+                           const etai_attn_ctrl* ctrl, void* eps_out, void* stream);
+
 /* ---- null-text inversion: gradient of the UNet output w.r.t. the text context ------------------------------------
  * replaces `loss.backward()` through `unet(latent_cur, t, uncond_embeddings)` at
  * modules/inversion/null_text_inversion.py:75-80 (the only differentiated input is the [1,77,768] uncond embedding).
