@@ -50,6 +50,12 @@ def test_no_gpu_is_a_loud_error_not_a_fallback():
         engine.UNetEngine({}, dtype=torch.float32)
     with pytest.raises(RuntimeError):
         engine.gemm(torch.zeros(4, 64), torch.zeros(4, 64))
+    with pytest.raises(RuntimeError, match="CUDA"):  # the proximal CFG has no torch fallback either
+        engine.prox_guidance(torch.zeros(1, 4, 8, 8), torch.zeros(1, 4, 8, 8), 7.5, 0.7)
+    # argument errors come back as codes + text, never as a crash: null pointers, ranks outside the tensor
+    assert lib.etai_prox_guidance(None, None, None, 16, 3, 4, 0.5, 0.0, 0, 7.5, None, None) < 0
+    assert b"prox_guidance" in lib.etai_last_error()
+    assert lib.etai_unet_forward_rows(None, None, None, 0, 2, None, None, None) < 0
     import eta_inversion_b200 as etai
     with pytest.raises(RuntimeError):
         etai.load_diffusion_model("synthetic-sd15", "cpu")
