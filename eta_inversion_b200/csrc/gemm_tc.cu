@@ -8,9 +8,10 @@
 // bw x bh x bb = 128 output pixels (64x2, 32x4, 16x8 or 8x8x2 images), which lands in shared memory in exactly the
 // K-major / 128B-swizzled layout the UMMA descriptor expects.
 //
-// CTA = 192 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> fused epilogue -> global).  smem ring of STAGES x (A 128x64 + B BNx64).
-// UMMA shape 128 x BN x 16 (cta_group::1), BN in {128, 160}.  Roofline: tensor pipe.
+// CTA = 320 threads: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..9 = epilogue (TMEM -> registers -> fused epilogue -> shared-memory panels -> TMA store).  smem ring of
+// STAGES x (A 128x64 + B BNx64).  UMMA shape 128 x UN x 16 (cta_group::1), UN in {128, 160}; a 320-wide tile is two
+// 160-wide accumulators.  Roofline: tensor pipe (see DESIGN.md section 5 for what the per-role clock trace shows).
 #include <algorithm>
 #include <mutex>
 #include <vector>
